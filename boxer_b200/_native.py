@@ -1,0 +1,129 @@
+"""Loader / builder of the C-ABI library ``libboxattn_b200.so`` (include/boxattn_b200.h).
+
+The library is built in-tree (``boxer_b200/_C/``) by ``build()`` with nvcc for
+sm_100a only.  There is no CPU or PyTorch fallback: if the library is missing
+or a symbol the header declares is absent, importing callers get an
+``ImportError`` / ``RuntimeError`` -- never a silently different code path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_PKG)
+CSRC = os.path.join(_PKG, "csrc")
+LIB_DIR = os.path.join(_PKG, "_C")
+LIB_PATH = os.path.join(LIB_DIR, "libboxattn_b200.so")
+HEADER = os.path.join(ROOT, "include", "boxattn_b200.h")
+SOURCES = [os.path.join(CSRC, "boxattn_abi.cu")]
+DEPENDS = SOURCES + [os.path.join(CSRC, "boxattn_kernels.cuh"), os.path.join(CSRC, "boxattn_fused.cuh"), HEADER]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--compiler-options", "-fPIC",
+    "-shared",
+]
+
+DTYPES = ("f32", "f64", "bf16")
+OPS = ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd")
+EXPORTS = (
+    ["bxr_abi_version", "bxr_status_string", "bxr_last_error_detail", "bxr_last_launch_count",
+     "bxr_attn_bwd_workspace_bytes"]
+    + [f"bxr_{op}_{dt}" for op in OPS for dt in DTYPES]
+)
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libboxattn_b200.so")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in DEPENDS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into boxer_b200/_C/libboxattn_b200.so."""
+    with _lock:
+        if not force and not is_stale():
+            return LIB_PATH
+        os.makedirs(LIB_DIR, exist_ok=True)
+        tmp = LIB_PATH + ".tmp"
+        cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+        if verbose:
+            print(proc.stderr)
+        os.replace(tmp, LIB_PATH)
+        return LIB_PATH
+
+
+def _declare(lib):
+    c = ctypes
+    lib.bxr_abi_version.restype = c.c_int
+    lib.bxr_status_string.restype = c.c_char_p
+    lib.bxr_status_string.argtypes = [c.c_int]
+    lib.bxr_last_error_detail.restype = c.c_char_p
+    lib.bxr_last_launch_count.restype = c.c_int
+    lib.bxr_attn_bwd_workspace_bytes.restype = c.c_size_t
+    lib.bxr_attn_bwd_workspace_bytes.argtypes = [c.c_int] * 5 + [c.c_uint]
+    vp, i, u, sz = c.c_void_p, c.c_int, c.c_uint, c.c_size_t
+    dims = [i] * 7
+    for dt in DTYPES:
+        f = getattr(lib, f"bxr_box_attn_fwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 5 + dims + [vp, u, vp]
+        f = getattr(lib, f"bxr_box_attn_bwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 6 + dims + [vp] * 3 + [vp, sz, u, vp]
+        f = getattr(lib, f"bxr_instance_attn_fwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 6 + dims + [vp, vp, u, vp]
+        f = getattr(lib, f"bxr_instance_attn_bwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 8 + dims + [vp] * 4 + [vp, sz, u, vp]
+    return lib
+
+
+def load():
+    """dlopen the in-tree library; raises if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+                    "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                    "boxer_b200 has no CPU / PyTorch fallback."
+                )
+            lib = ctypes.CDLL(LIB_PATH)
+            missing = [s for s in EXPORTS if not hasattr(lib, s)]
+            if missing:
+                raise ImportError(f"{LIB_PATH} does not export {missing}; rebuild it")
+            if lib.bxr_abi_version() != 1:
+                raise ImportError("libboxattn_b200.so ABI version mismatch; rebuild it")
+            _lib = _declare(lib)
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        lib = load()
+        name = lib.bxr_status_string(status).decode()
+        detail = lib.bxr_last_error_detail().decode()
+        raise RuntimeError(f"{what} failed: {name}" + (f" ({detail})" if detail else ""))

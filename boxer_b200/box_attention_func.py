@@ -1,0 +1,129 @@
+"""``BoxAttnFunction`` / ``InstanceAttnFunction``: the autograd boundary.
+
+Drop-in for ``/root/reference/e2edet/module/ops/box_attention_func.py:9-150``:
+same class names, same ``apply`` argument order, same outputs, same
+``(grad, None, None, grad, grad, None...)`` backward tuples, same AMP contract
+(``custom_fwd(cast_inputs=torch.float32)``: under autocast the op runs in fp32),
+``once_differentiable``.  The native calls go to ``boxer_b200.ops`` (C ABI).
+
+Beyond the reference: ``BoxAttnBf16Function`` / ``InstanceAttnBf16Function`` keep
+``value`` / outputs in bfloat16 (locations and weights fp32, fp32 accumulation) --
+an explicit opt-in used by the modules when ``boxer_b200.set_amp_native(True)``.
+"""
+from __future__ import annotations
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+class BoxAttnFunction(Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ops.box_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                      sampling_locations, attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_contiguous():
+            grad_output = grad_output.contiguous()
+        value, shapes, lsi, loc, attn = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = ops.box_attn_backward(
+            value, shapes, lsi, loc, attn, grad_output.to(value.dtype), ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None
+
+
+class InstanceAttnFunction(Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                spatial_attention_weights, level_attention_weights, mask_size, im2col_step):
+        ctx.im2col_step = im2col_step
+        output, mask_output = ops.instance_attn_forward(
+            value, value_spatial_shapes, value_level_start_index, sampling_locations,
+            spatial_attention_weights, level_attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              spatial_attention_weights, level_attention_weights)
+        b, l, _, c = mask_output.shape
+        mask_output = mask_output.view(b, l, mask_size, mask_size, c)
+        return output, mask_output
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, grad_output, grad_mask_output):
+        if not grad_output.is_contiguous():
+            grad_output = grad_output.contiguous()
+        if not grad_mask_output.is_contiguous():
+            grad_mask_output = grad_mask_output.contiguous()
+        value, shapes, lsi, loc, sw, lw = ctx.saved_tensors
+        grad_value, grad_loc, grad_sw, grad_lw = ops.instance_attn_backward(
+            value, shapes, lsi, loc, sw, lw, grad_output.to(value.dtype), grad_mask_output.to(value.dtype),
+            ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_sw, grad_lw, None, None
+
+
+# --------------------------------------------------------------------------- bf16 opt-in
+def _bf16_inputs(value, loc, *weights):
+    return (value.to(torch.bfloat16).contiguous(), loc.float().contiguous(),
+            *[w.float().contiguous() for w in weights])
+
+
+class BoxAttnBf16Function(Function):
+    """value / out in bf16, loc and weights fp32, fp32 accumulation.  Gradients come back in
+    the dtypes of the tensors that were passed in."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, lsi, loc, attn, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.in_dtypes = (value.dtype, loc.dtype, attn.dtype)
+        with torch.autocast("cuda", enabled=False):
+            v, l, a = _bf16_inputs(value, loc, attn)
+            out = ops.box_attn_forward(v, shapes, lsi, l, a, im2col_step)
+        ctx.save_for_backward(v, shapes, lsi, l, a)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        v, shapes, lsi, l, a = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            gv, gl, ga = ops.box_attn_backward(v, shapes, lsi, l, a, grad_output.to(torch.bfloat16).contiguous(),
+                                               ctx.im2col_step)
+        dv, dl, da = ctx.in_dtypes
+        return gv.to(dv), None, None, gl.to(dl), ga.to(da).view_as(a), None
+
+
+class InstanceAttnBf16Function(Function):
+    @staticmethod
+    def forward(ctx, value, shapes, lsi, loc, sw, lw, mask_size, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.in_dtypes = (value.dtype, loc.dtype, sw.dtype, lw.dtype)
+        with torch.autocast("cuda", enabled=False):
+            v, l, s, w = _bf16_inputs(value, loc, sw, lw)
+            out, mask = ops.instance_attn_forward(v, shapes, lsi, l, s, w, im2col_step)
+        ctx.save_for_backward(v, shapes, lsi, l, s, w)
+        b, nq, _, c = mask.shape
+        return out, mask.view(b, nq, mask_size, mask_size, c)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output, grad_mask_output):
+        v, shapes, lsi, l, s, w = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            gv, gl, gs, gw = ops.instance_attn_backward(
+                v, shapes, lsi, l, s, w, grad_output.to(torch.bfloat16).contiguous(),
+                grad_mask_output.to(torch.bfloat16).contiguous(), ctx.im2col_step)
+        dv, dl, ds, dw = ctx.in_dtypes
+        return gv.to(dv), None, None, gl.to(dl), gs.to(ds), gw.to(dw), None, None

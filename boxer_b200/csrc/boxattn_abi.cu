@@ -1,0 +1,380 @@
+// Host side of the C ABI declared in include/boxattn_b200.h: argument checks, path selection,
+// launch geometry.  Pure CUDA runtime -- no torch / ATen here.
+//
+// Replaces the reference's host functions (e2edet/module/ops/src/box_attn/box_attn.cu:15-135,
+// instance_attn/instance_attn.cu:15-157): same inputs, but the caller owns all memory, there is
+// no im2col_step chunk loop (every image goes in one launch), and failures are returned.
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+
+#include "boxattn_kernels.cuh"
+#include "../../include/boxattn_b200.h"
+
+namespace {
+
+using namespace bxr;
+
+thread_local char g_detail[256] = "";
+thread_local int g_launches = 0;
+
+int fail(int status, const char* what) {
+    snprintf(g_detail, sizeof(g_detail), "%s", what);
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_detail, sizeof(g_detail), "%s: %s", where, cudaGetErrorString(e));
+    return BXR_ERR_CUDA;
+}
+
+#define BXR_CUDA(expr)                                        \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+    } while (0)
+
+int sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+template <void (*K)(const AttnParams)>
+int ctas_per_sm() {
+    static int occ = 0;   // immutable once set; a benign race only recomputes the same number
+    if (occ == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, kThreads, 0) != cudaSuccess || n <= 0) n = 1;
+        occ = n;
+    }
+    return occ;
+}
+
+template <void (*K)(const AttnParams)>
+int launch(const AttnParams& p, int grid, cudaStream_t st, const char* name) {
+    K<<<grid, kThreads, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    ++g_launches;
+    return BXR_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+int check_dims(int B, int S, int H, int D, int L, int Nq, int P) {
+    if (B < 0 || S < 0 || H < 0 || D < 0 || L < 0 || Nq < 0 || P < 0) return fail(BXR_ERR_BAD_DIM, "negative dimension");
+    if (L > BXR_MAX_LEVELS) return fail(BXR_ERR_BAD_DIM, "L exceeds BXR_MAX_LEVELS");
+    if ((long long)L * P > 0x7fffffffLL / 4) return fail(BXR_ERR_BAD_DIM, "L*P too large");
+    return BXR_OK;
+}
+
+// lanes per row of the vector path, or 0 when it does not apply
+template <typename TV>
+int vec_group(int D, int LP) {
+    if (std::is_same<TV, double>::value) return 0;
+    const int vec = 16 / (int)sizeof(TV);
+    if (D <= 0 || D % vec) return 0;
+    const int g = D / vec;
+    if (g > 32 || (g & (g - 1))) return 0;
+    if (LP >= 65536) return 0;
+    return g;
+}
+
+// Split a row's points over several lane groups when there are too few rows to fill the GPU
+// (decoder calls: 300 queries x 8 heads; the mask head has 4*196 points per row).
+void choose_split(AttnParams& p, int G, int lim, int min_chunk) {
+    const int groups = kThreads / G;
+    const long long want_units = 4LL * sm_count();
+    int k = 0;
+    while ((1 << (k + 1)) <= groups && (lim >> (k + 1)) >= min_chunk &&
+           (p.rows << k) / groups < want_units)
+        ++k;
+    p.nsplit_log2 = k;
+    const int ns = 1 << k;
+    p.chunk = (lim + ns - 1) / ns;
+    const int rows_per_unit = groups >> k;
+    p.units = (int)((p.rows + rows_per_unit - 1) / rows_per_unit);
+}
+
+template <void (*K)(const AttnParams)>
+int launch_units(const AttnParams& p, cudaStream_t st, const char* name) {
+    int grid = sm_count() * ctas_per_sm<K>();
+    if (grid > p.units) grid = p.units;
+    if (grid < 1) grid = 1;
+    return launch<K>(p, grid, st, name);
+}
+
+template <void (*K)(const AttnParams)>
+int launch_rows(const AttnParams& p, cudaStream_t st, const char* name) {
+    const long long warps = kThreads / 32;
+    long long grid = (p.rows + warps - 1) / warps;
+    const long long cap = (long long)sm_count() * ctas_per_sm<K>() * 4;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    return launch<K>(p, (int)grid, st, name);
+}
+
+template <typename TV, bool INSTANCE, int G>
+int fwd_vec(AttnParams& p, cudaStream_t st) {
+    constexpr int U = (sizeof(TV) == 2) ? 2 : 4;
+    choose_split(p, G, INSTANCE ? p.P : p.LP, INSTANCE ? 2 : 2 * U);
+    if (!INSTANCE) p.chunk = (p.chunk + U - 1) / U * U;   // whole batches; the tail is masked by j < j1
+    return launch_units<attn_fwd_vec_kernel<TV, G, INSTANCE, U>>(p, st, "attn_fwd_vec_kernel");
+}
+
+template <typename TV, bool INSTANCE, typename ACC, int G>
+int bwd_vec(AttnParams& p, cudaStream_t st) {
+    choose_split(p, G, INSTANCE ? p.P : p.LP, INSTANCE ? 2 : 4);
+    return launch_units<attn_bwd_vec_kernel<TV, G, INSTANCE, ACC>>(p, st, "attn_bwd_vec_kernel");
+}
+
+#define BXR_DISPATCH_G(G_, CALL)                                  \
+    switch (G_) {                                                 \
+        case 1: { constexpr int G = 1; return CALL; }             \
+        case 2: { constexpr int G = 2; return CALL; }             \
+        case 4: { constexpr int G = 4; return CALL; }             \
+        case 8: { constexpr int G = 8; return CALL; }             \
+        case 16: { constexpr int G = 16; return CALL; }           \
+        default: { constexpr int G = 32; return CALL; }           \
+    }
+
+template <typename TV, bool INSTANCE>
+int dispatch_fwd_vec(int g, AttnParams& p, cudaStream_t st) {
+    BXR_DISPATCH_G(g, (fwd_vec<TV, INSTANCE, G>(p, st)))
+}
+template <typename TV, bool INSTANCE, typename ACC>
+int dispatch_bwd_vec(int g, AttnParams& p, cudaStream_t st) {
+    BXR_DISPATCH_G(g, (bwd_vec<TV, INSTANCE, ACC, G>(p, st)))
+}
+
+void fill_sizes(AttnParams& p, int B, int S, int H, int D, int L, int Nq, int P) {
+    p.B = B; p.S = S; p.H = H; p.D = D; p.L = L; p.Nq = Nq; p.P = P;
+    p.LP = L * P;
+    p.magicP = P > 1 ? (unsigned)((0x100000000ULL + (unsigned)P - 1) / (unsigned)P) : 0u;
+    p.rows = (long long)B * Nq * H;
+    p.nsplit_log2 = 0;
+    p.chunk = p.LP;
+    p.units = 0;
+}
+
+template <typename TV, typename TW, bool INSTANCE>
+int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, const TW* w0, const TW* w1,
+            int B, int S, int H, int D, int L, int Nq, int P, TV* out, TV* mask_out, unsigned flags, bxr_stream_t stream) {
+    g_launches = 0;
+    g_detail[0] = 0;
+    (void)flags;
+    if (int s = check_dims(B, S, H, D, L, Nq, P)) return s;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    fill_sizes(p, B, S, H, D, L, Nq, P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p.rows == 0 || D == 0) return BXR_OK;
+    if (!out || (INSTANCE && !mask_out && P > 0)) return fail(BXR_ERR_NULL_POINTER, "output pointer is NULL");
+    if (p.LP == 0 || S == 0) {   // nothing to sample: outputs are all zero
+        BXR_CUDA(cudaMemsetAsync(out, 0, sizeof(TV) * (size_t)p.rows * D, st));
+        if (INSTANCE && P > 0) BXR_CUDA(cudaMemsetAsync(mask_out, 0, sizeof(TV) * (size_t)p.rows * D * P, st));
+        return BXR_OK;
+    }
+    if (!value || !shapes || !level_start || !loc || !w0 || (INSTANCE && !w1))
+        return fail(BXR_ERR_NULL_POINTER, "input pointer is NULL");
+    p.value = value; p.shapes = shapes; p.level_start = level_start;
+    p.loc = loc; p.w0 = w0; p.w1 = w1; p.out = out; p.mask_out = mask_out;
+
+    const int g = vec_group<TV>(D, p.LP);
+    if (g && aligned16(value) && aligned16(out) && (!INSTANCE || aligned16(mask_out)) && aligned8(loc)) {
+        if constexpr (!std::is_same<TV, double>::value) return dispatch_fwd_vec<TV, INSTANCE>(g, p, st);
+    }
+    return launch_rows<attn_fwd_gen_kernel<TV, INSTANCE>>(p, st, "attn_fwd_gen_kernel");
+}
+
+constexpr size_t kWsHeader = 256;   // absmax bits[4] + scale, kept apart from the accumulator
+
+size_t workspace_bytes(int dtype_bytes, long long n, unsigned flags) {
+    if (n <= 0) return 0;
+    if (flags & BXR_FLAG_DETERMINISTIC) return kWsHeader + 8 * (size_t)n;
+    if (dtype_bytes == 2) return 4 * (size_t)n;
+    return 0;
+}
+
+template <typename T>
+int absmax(const T* x, long long n, unsigned* bits, cudaStream_t st) {
+    if (n <= 0) return BXR_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+    absmax_kernel<T><<<(int)blocks, 256, 0, st>>>(x, n, bits);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
+    ++g_launches;
+    return BXR_OK;
+}
+
+template <typename TV, typename ACC>
+int finalize(const ACC* acc, TV* out, long long n, const float* scale, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    finalize_grad_value_kernel<TV, ACC><<<(int)blocks, 256, 0, st>>>(acc, out, n, scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "finalize_grad_value_kernel");
+    ++g_launches;
+    return BXR_OK;
+}
+
+template <typename TV, typename TW, bool INSTANCE>
+int backward(const TV* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, const TW* w0, const TW* w1,
+             const TV* grad_out, const TV* grad_mask, int B, int S, int H, int D, int L, int Nq, int P,
+             TV* grad_value, TW* grad_loc, TW* grad_w0, TW* grad_w1,
+             void* workspace, size_t workspace_bytes_given, unsigned flags, bxr_stream_t stream) {
+    using TC = typename Compute<TV>::type;
+    g_launches = 0;
+    g_detail[0] = 0;
+    if (int s = check_dims(B, S, H, D, L, Nq, P)) return s;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    fill_sizes(p, B, S, H, D, L, Nq, P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n_value = (long long)B * S * H * D;
+    const bool det = (flags & BXR_FLAG_DETERMINISTIC) != 0;
+    if (n_value > 0) {
+        if (!grad_value) return fail(BXR_ERR_NULL_POINTER, "grad_value is NULL");
+        BXR_CUDA(cudaMemsetAsync(grad_value, 0, sizeof(TV) * (size_t)n_value, st));
+    }
+    if (p.rows == 0 || p.LP == 0) return BXR_OK;
+    if (!grad_loc || !grad_w0 || (INSTANCE && !grad_w1)) return fail(BXR_ERR_NULL_POINTER, "gradient pointer is NULL");
+    if (D == 0 || S == 0) {   // no channels / no pixels: all gradients are zero
+        BXR_CUDA(cudaMemsetAsync(grad_loc, 0, sizeof(TW) * (size_t)p.rows * p.LP * 2, st));
+        BXR_CUDA(cudaMemsetAsync(grad_w0, 0, sizeof(TW) * (size_t)p.rows * p.LP, st));
+        if (INSTANCE) BXR_CUDA(cudaMemsetAsync(grad_w1, 0, sizeof(TW) * (size_t)p.rows * p.LP, st));
+        return BXR_OK;
+    }
+    if (!value || !shapes || !level_start || !loc || !w0 || !grad_out || (INSTANCE && (!w1 || !grad_mask)))
+        return fail(BXR_ERR_NULL_POINTER, "input pointer is NULL");
+
+    const size_t need = workspace_bytes((int)sizeof(TV), n_value, flags);
+    if (need && (!workspace || workspace_bytes_given < need)) return fail(BXR_ERR_WORKSPACE, "workspace too small");
+    if (need && !aligned16(workspace)) return fail(BXR_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+
+    p.value = value; p.shapes = shapes; p.level_start = level_start;
+    p.loc = loc; p.w0 = w0; p.w1 = w1; p.grad_out = grad_out; p.grad_mask = grad_mask;
+    p.grad_loc = grad_loc; p.grad_w0 = grad_w0; p.grad_w1 = grad_w1;
+
+    unsigned* bits = nullptr;
+    float* scale = nullptr;
+    void* acc = grad_value;
+    if (det) {
+        bits = static_cast<unsigned*>(workspace);
+        scale = reinterpret_cast<float*>(bits + 4);
+        acc = static_cast<char*>(workspace) + kWsHeader;
+        BXR_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+        if (int s = absmax<TV>(grad_out, p.rows * D, bits + 0, st)) return s;
+        if (int s = absmax<TW>(w0, p.rows * p.LP, bits + 1, st)) return s;
+        if (INSTANCE) {
+            if (int s = absmax<TV>(grad_mask, p.rows * D * P, bits + 2, st)) return s;
+            if (int s = absmax<TW>(w1, p.rows * p.LP, bits + 3, st)) return s;
+        }
+        det_scale_kernel<<<1, 1, 0, st>>>(bits, scale);
+        BXR_CUDA(cudaGetLastError());
+        ++g_launches;
+        p.det_scale = scale;
+    } else if (sizeof(TV) == 2) {
+        acc = workspace;
+        BXR_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    }
+    p.grad_value_acc = acc;
+
+    int status;
+    const int g = vec_group<TV>(D, p.LP);
+    const bool vec_ok = g && aligned16(value) && aligned16(grad_out) && aligned16(acc) && (!INSTANCE || aligned16(grad_mask)) &&
+                        aligned8(loc) && aligned8(grad_loc);
+    if constexpr (!std::is_same<TV, double>::value) {
+        if (vec_ok) {
+            status = det ? dispatch_bwd_vec<TV, INSTANCE, long long>(g, p, st) : dispatch_bwd_vec<TV, INSTANCE, float>(g, p, st);
+        } else {
+            status = det ? launch_rows<attn_bwd_gen_kernel<TV, INSTANCE, long long>>(p, st, "attn_bwd_gen_kernel")
+                         : launch_rows<attn_bwd_gen_kernel<TV, INSTANCE, TC>>(p, st, "attn_bwd_gen_kernel");
+        }
+    } else {
+        status = det ? launch_rows<attn_bwd_gen_kernel<TV, INSTANCE, long long>>(p, st, "attn_bwd_gen_kernel")
+                     : launch_rows<attn_bwd_gen_kernel<TV, INSTANCE, TC>>(p, st, "attn_bwd_gen_kernel");
+    }
+    if (status) return status;
+
+    if (det) return finalize<TV, long long>(static_cast<const long long*>(acc), grad_value, n_value, scale, st);
+    if (sizeof(TV) == 2) return finalize<TV, float>(static_cast<const float*>(acc), grad_value, n_value, nullptr, st);
+    return BXR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bxr_abi_version(void) { return BXR_ABI_VERSION; }
+
+const char* bxr_status_string(int status) {
+    switch (status) {
+        case BXR_OK: return "ok";
+        case BXR_ERR_NULL_POINTER: return "null pointer";
+        case BXR_ERR_BAD_DIM: return "bad dimension";
+        case BXR_ERR_WORKSPACE: return "workspace missing, too small or misaligned";
+        case BXR_ERR_CUDA: return "CUDA error";
+        case BXR_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+const char* bxr_last_error_detail(void) { return g_detail; }
+int bxr_last_launch_count(void) { return g_launches; }
+
+size_t bxr_attn_bwd_workspace_bytes(int dtype_bytes, int B, int S, int H, int D, unsigned flags) {
+    if (B < 0 || S < 0 || H < 0 || D < 0) return 0;
+    return workspace_bytes(dtype_bytes, (long long)B * S * H * D, flags);
+}
+
+#define BXR_DEFINE_OPS(SUF, TVABI, TV, TW)                                                                           \
+    int bxr_box_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, \
+                               const TW* attn, int B, int S, int H, int D, int L, int Nq, int P, TVABI* out,         \
+                               unsigned flags, bxr_stream_t stream) {                                                \
+        return forward<TV, TW, false>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, attn, nullptr,   \
+                                      B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out), nullptr, flags, stream);     \
+    }                                                                                                                \
+    int bxr_box_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, \
+                               const TW* attn, const TVABI* grad_out, int B, int S, int H, int D, int L, int Nq,     \
+                               int P, TVABI* grad_value, TW* grad_loc, TW* grad_attn, void* workspace,               \
+                               size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {                        \
+        return backward<TV, TW, false>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, attn, nullptr,  \
+                                       reinterpret_cast<const TV*>(grad_out), nullptr, B, S, H, D, L, Nq, P,         \
+                                       reinterpret_cast<TV*>(grad_value), grad_loc, grad_attn, nullptr, workspace,   \
+                                       workspace_bytes, flags, stream);                                              \
+    }                                                                                                                \
+    int bxr_instance_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
+                                    const TW* loc, const TW* spatial_w, const TW* level_w, int B, int S, int H,      \
+                                    int D, int L, int Nq, int P, TVABI* out, TVABI* mask_out, unsigned flags,        \
+                                    bxr_stream_t stream) {                                                           \
+        return forward<TV, TW, true>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, spatial_w,        \
+                                     level_w, B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out),                      \
+                                     reinterpret_cast<TV*>(mask_out), flags, stream);                                \
+    }                                                                                                                \
+    int bxr_instance_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
+                                    const TW* loc, const TW* spatial_w, const TW* level_w, const TVABI* grad_out,    \
+                                    const TVABI* grad_mask, int B, int S, int H, int D, int L, int Nq, int P,        \
+                                    TVABI* grad_value, TW* grad_loc, TW* grad_spatial_w, TW* grad_level_w,           \
+                                    void* workspace, size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {  \
+        return backward<TV, TW, true>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, spatial_w,       \
+                                      level_w, reinterpret_cast<const TV*>(grad_out),                                \
+                                      reinterpret_cast<const TV*>(grad_mask), B, S, H, D, L, Nq, P,                  \
+                                      reinterpret_cast<TV*>(grad_value), grad_loc, grad_spatial_w, grad_level_w,     \
+                                      workspace, workspace_bytes, flags, stream);                                    \
+    }
+
+BXR_DEFINE_OPS(f32, float, float, float)
+BXR_DEFINE_OPS(f64, double, double, double)
+BXR_DEFINE_OPS(bf16, bxr_bf16, __nv_bfloat16, float)
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+"""Tensor-level entry points: the mirror of the reference's pybind module ``e2edet.ops``.
+
+Same four functions, same argument order and return values as
+``/root/reference/e2edet/module/ops/src/vision.cpp:7-12``:
+
+    box_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step) -> output
+    box_attn_backward(..., grad_output, im2col_step) -> [grad_value, grad_sampling_loc, grad_attn_weight]
+    instance_attn_forward(value, shapes, lsi, loc, spatial_attn_weight, level_attn_weight, im2col_step) -> [output, mask_output]
+    instance_attn_backward(..., grad_output, grad_mask_output, im2col_step) -> [grad_value, grad_loc, grad_spatial, grad_level]
+
+PyTorch is used here only to allocate device memory and to name the stream; the
+arithmetic is in ``libboxattn_b200.so`` (include/boxattn_b200.h) and nowhere
+else -- there is no CPU implementation (the reference has none either:
+``box_attn.h:53`` "Not implemented on the CPU") and no fallback.
+
+Behavioural notes vs the reference host code (box_attn.cu:15-135):
+* non-CUDA or non-contiguous inputs raise ``RuntimeError`` (reference: AT_ASSERTM);
+* ``batch % min(batch, im2col_step) == 0`` is still required (box_attn.cu:40-42), but the
+  chunk loop is gone: every image goes in one launch;
+* kernel launch failures raise (the reference printf()s them, box_attn_kernel.cuh:1118-1122);
+* shape mismatches between loc / weights / value raise instead of reading out of bounds;
+* dtypes: float32, float64 and -- beyond the reference -- bfloat16 ``value`` (loc / weights
+  stay float32; accumulation fp32).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native
+
+_DET_OVERRIDE = None          # None: follow torch.are_deterministic_algorithms_enabled()
+FLAG_DETERMINISTIC = 0x1
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
+
+
+def set_deterministic(mode):
+    """True / False: force the bit-reproducible (fixed-point) or the atomic grad_value scatter.
+    None (default): follow ``torch.are_deterministic_algorithms_enabled()``."""
+    global _DET_OVERRIDE
+    _DET_OVERRIDE = mode
+
+
+def deterministic() -> bool:
+    if _DET_OVERRIDE is not None:
+        return bool(_DET_OVERRIDE)
+    return torch.are_deterministic_algorithms_enabled()
+
+
+def last_launch_count() -> int:
+    """Kernels enqueued by this thread's last native call (bench.py's gpu_launches)."""
+    return int(_native.load().bxr_last_launch_count())
+
+
+# ------------------------------------------------------------------ checks
+def _check_input(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _geometry(value, shapes, lsi, loc, weights):
+    for t, n in ((value, "value"), (shapes, "spatial_shapes"), (lsi, "level_start_index"), (loc, "sampling_loc")):
+        _check_input(t, n)
+    for i, w in enumerate(weights):
+        _check_input(w, f"attn_weight[{i}]")
+    if value.dim() != 4:
+        raise RuntimeError(f"value must be (B, S, heads, head_dim), got {tuple(value.shape)}")
+    if shapes.dtype != torch.int64 or lsi.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64")
+    if shapes.dim() != 2 or shapes.shape[1] != 2:
+        raise RuntimeError(f"spatial_shapes must be (L, 2), got {tuple(shapes.shape)}")
+    B, S, H, D = value.shape
+    L = shapes.shape[0]
+    if lsi.numel() != L:
+        raise RuntimeError("level_start_index must have one entry per level")
+    if loc.dim() != 6 or loc.shape[0] != B or loc.shape[2] != H or loc.shape[3] != L or loc.shape[5] != 2:
+        raise RuntimeError(
+            f"sampling_loc must be (B={B}, Nq, heads={H}, L={L}, P, 2), got {tuple(loc.shape)}")
+    Nq, P = loc.shape[1], loc.shape[4]
+    for w in weights:
+        if w.numel() != B * Nq * H * L * P:
+            raise RuntimeError(
+                f"attention weights must hold B*Nq*heads*L*P = {B * Nq * H * L * P} elements, got {tuple(w.shape)}")
+    if L > 32:
+        raise RuntimeError("at most 32 levels are supported")
+    devs = {t.device for t in (value, shapes, lsi, loc, *weights)}
+    if len(devs) != 1:
+        raise RuntimeError(f"all tensors must be on the same device, got {sorted(map(str, devs))}")
+    return B, S, H, D, L, Nq, P
+
+
+def _dtypes(value, loc, weights):
+    """(suffix, TW dtype).  value decides; loc/weights must already be the matching TW."""
+    suf = _SUFFIX.get(value.dtype)
+    if suf is None:
+        raise RuntimeError(f"box attention supports float32, float64 and bfloat16 value, got {value.dtype}")
+    tw = torch.float64 if value.dtype == torch.float64 else torch.float32
+    for t in (loc, *weights):
+        if t.dtype != tw:
+            raise RuntimeError(f"with {value.dtype} value, sampling_loc and weights must be {tw}, got {t.dtype}")
+    return suf, tw
+
+
+def _step_check(B, im2col_step):
+    step = min(B, int(im2col_step))
+    if B > 0 and (step <= 0 or B % step != 0):
+        raise RuntimeError(f"batch({B}) must divide im2col_step({step})")
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _workspace(lib, value, flags):
+    B, S, H, D = value.shape
+    n = lib.bxr_attn_bwd_workspace_bytes(value.element_size(), B, S, H, D, flags)
+    if not n:
+        return None, 0
+    return torch.empty(n, dtype=torch.uint8, device=value.device), n
+
+
+# ------------------------------------------------------------------ box op
+def box_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64):
+    B, S, H, D, L, Nq, P = _geometry(value, spatial_shapes, level_start_index, sampling_loc, (attn_weight,))
+    suf, _ = _dtypes(value, sampling_loc, (attn_weight,))
+    _step_check(B, im2col_step)
+    lib = _native.load()
+    out = torch.empty((B, Nq, H * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        st = getattr(lib, f"bxr_box_attn_fwd_{suf}")(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), B, S, H, D, L, Nq, P,
+            out.data_ptr(), 0, _stream(value.device))
+    _native.check(st, "box_attn_forward")
+    return out
+
+
+def box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step=64):
+    B, S, H, D, L, Nq, P = _geometry(value, spatial_shapes, level_start_index, sampling_loc, (attn_weight,))
+    suf, _ = _dtypes(value, sampling_loc, (attn_weight,))
+    _check_input(grad_output, "grad_output")
+    if grad_output.dtype != value.dtype or grad_output.numel() != B * Nq * H * D:
+        raise RuntimeError("grad_output must match the forward output's dtype and size")
+    _step_check(B, im2col_step)
+    lib = _native.load()
+    flags = FLAG_DETERMINISTIC if deterministic() else 0
+    grad_value = torch.empty_like(value)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device):
+        ws, ws_bytes = _workspace(lib, value, flags)
+        st = getattr(lib, f"bxr_box_attn_bwd_{suf}")(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+            B, S, H, D, L, Nq, P,
+            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+            ws.data_ptr() if ws is not None else None, ws_bytes, flags, _stream(value.device))
+    _native.check(st, "box_attn_backward")
+    return [grad_value, grad_loc, grad_attn]
+
+
+# ------------------------------------------------------------- instance op
+def instance_attn_forward(value, spatial_shapes, level_start_index, sampling_loc,
+                          spatial_attn_weight, level_attn_weight, im2col_step=64):
+    ws_ = (spatial_attn_weight, level_attn_weight)
+    B, S, H, D, L, Nq, P = _geometry(value, spatial_shapes, level_start_index, sampling_loc, ws_)
+    suf, _ = _dtypes(value, sampling_loc, ws_)
+    _step_check(B, im2col_step)
+    lib = _native.load()
+    out = torch.empty((B, Nq, H * D), dtype=value.dtype, device=value.device)
+    mask_out = torch.empty((B, Nq, P, H * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        st = getattr(lib, f"bxr_instance_attn_fwd_{suf}")(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), spatial_attn_weight.data_ptr(), level_attn_weight.data_ptr(),
+            B, S, H, D, L, Nq, P, out.data_ptr(), mask_out.data_ptr(), 0, _stream(value.device))
+    _native.check(st, "instance_attn_forward")
+    return [out, mask_out]
+
+
+def instance_attn_backward(value, spatial_shapes, level_start_index, sampling_loc,
+                           spatial_attn_weight, level_attn_weight, grad_output, grad_mask_output, im2col_step=64):
+    ws_ = (spatial_attn_weight, level_attn_weight)
+    B, S, H, D, L, Nq, P = _geometry(value, spatial_shapes, level_start_index, sampling_loc, ws_)
+    suf, _ = _dtypes(value, sampling_loc, ws_)
+    _check_input(grad_output, "grad_output")
+    _check_input(grad_mask_output, "grad_mask_output")
+    if grad_output.dtype != value.dtype or grad_output.numel() != B * Nq * H * D:
+        raise RuntimeError("grad_output must match the forward output's dtype and size")
+    if grad_mask_output.dtype != value.dtype or grad_mask_output.numel() != B * Nq * P * H * D:
+        raise RuntimeError("grad_mask_output must match the forward mask output's dtype and size")
+    _step_check(B, im2col_step)
+    lib = _native.load()
+    flags = FLAG_DETERMINISTIC if deterministic() else 0
+    grad_value = torch.empty_like(value)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_sw = torch.empty_like(spatial_attn_weight)
+    grad_lw = torch.empty_like(level_attn_weight)
+    with torch.cuda.device(value.device):
+        ws, ws_bytes = _workspace(lib, value, flags)
+        st = getattr(lib, f"bxr_instance_attn_bwd_{suf}")(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), spatial_attn_weight.data_ptr(), level_attn_weight.data_ptr(),
+            grad_output.data_ptr(), grad_mask_output.data_ptr(),
+            B, S, H, D, L, Nq, P,
+            grad_value.data_ptr(), grad_loc.data_ptr(), grad_sw.data_ptr(), grad_lw.data_ptr(),
+            ws.data_ptr() if ws is not None else None, ws_bytes, flags, _stream(value.device))
+    _native.check(st, "instance_attn_backward")
+    return [grad_value, grad_loc, grad_sw, grad_lw]

@@ -1,0 +1,117 @@
+/*
+ * boxattn_b200 -- C ABI of the B200-native box-attention operators.
+ *
+ * This is the drop-in boundary for the hot path of kienduynguyen/BoxeR:
+ * the four native entry points the reference binds through pybind11
+ *
+ *   box_attn_forward / box_attn_backward           e2edet/module/ops/src/vision.cpp:8-9
+ *     -> e2edet::box_attn_cuda_forward/backward     e2edet/module/ops/src/box_attn/box_attn.cu:15-71, :74-135
+ *   instance_attn_forward / instance_attn_backward  e2edet/module/ops/src/vision.cpp:10-11
+ *     -> e2edet::instance_attn_cuda_forward/backward e2edet/module/ops/src/instance_attn/instance_attn.cu:15-82, :85-157
+ *
+ * re-stated as plain C: raw device pointers, sizes, a stream, an int status.
+ * No torch / ATen types cross this boundary.
+ *
+ * Contract
+ *   - Ownership: the CALLER allocates every buffer (outputs, gradients, workspace).
+ *     The library never allocates or frees device memory and never synchronises
+ *     the device or the stream; all work is enqueued on `stream`.
+ *   - Device: the current CUDA device of the calling thread (the host wrapper
+ *     sets it from the tensors).  Re-entrant, no mutable global state apart
+ *     from a per-device cache of immutable device attributes.
+ *   - Layouts are the reference's, all contiguous:
+ *       value        (B, S, H, D)          S = sum_l h_l*w_l, levels concatenated row-major (y, x)
+ *       shapes       (L, 2) int64 DEVICE   (h_l, w_l)            [read on the device, as the reference does,
+ *       level_start  (L,)   int64 DEVICE   first index of level l  box_attn_kernel.cuh:313-316 -- no D2H sync]
+ *       loc          (B, Nq, H, L, P, 2)   (x, y) normalised; pixel = loc * size - 0.5
+ *       attn / spatial_w / level_w (B, Nq, H, L, P)
+ *       out          (B, Nq, H*D)
+ *       mask_out     (B, Nq, P, H*D)       instance op only
+ *     Gradients have the layout of what they are the gradient of.
+ *   - Arithmetic: bilinear, zero padding, window test -1 < pixel < size
+ *     (box_attn_kernel.cuh:325-328), fp32 accumulation (fp64 for _f64).
+ *   - dtypes: _f32 (all tensors float), _f64 (all double; slow-is-fine, for
+ *     gradcheck), _bf16 (value / out / mask_out / grad_out / grad_mask /
+ *     grad_value are bfloat16 bits; loc, weights and their gradients float).
+ *   - Backward needs `grad_value` zero-filled: the library enqueues that memset
+ *     itself.  grad_loc / grad_* weights are fully overwritten.
+ *   - Errors: a non-zero bxr_status is returned (nothing is printed); the
+ *     reference only printf()s launch failures (box_attn_kernel.cuh:1118-1122).
+ *     bxr_status_string() names it, bxr_last_error_detail() gives the CUDA
+ *     error string of the calling thread's last failure.
+ *   - L <= BXR_MAX_LEVELS.
+ */
+#ifndef BOXATTN_B200_H_
+#define BOXATTN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BXR_ABI_VERSION 1
+#define BXR_MAX_LEVELS 32
+
+typedef enum bxr_status {
+    BXR_OK = 0,
+    BXR_ERR_NULL_POINTER = 1,   /* a required pointer is NULL */
+    BXR_ERR_BAD_DIM = 2,        /* negative dim, L > BXR_MAX_LEVELS, index range overflow */
+    BXR_ERR_WORKSPACE = 3,      /* workspace missing or smaller than *_workspace_bytes() */
+    BXR_ERR_CUDA = 4,           /* a CUDA runtime call or kernel launch failed */
+    BXR_ERR_UNSUPPORTED = 5     /* flag / dtype combination not available */
+} bxr_status;
+
+/* flags (bit set) */
+#define BXR_FLAG_DETERMINISTIC 0x1u /* backward: order-independent (bit-reproducible) grad_value scatter via
+                                       64-bit fixed-point accumulation instead of floating-point atomics */
+
+typedef void* bxr_stream_t;   /* a cudaStream_t */
+typedef uint16_t bxr_bf16;    /* raw bfloat16 bits */
+
+int bxr_abi_version(void);
+const char* bxr_status_string(int status);
+const char* bxr_last_error_detail(void);
+/* number of kernels (not memsets) the calling thread's last successful call enqueued */
+int bxr_last_launch_count(void);
+
+/* Bytes of scratch the backward calls need for these sizes / flags (0 = none).
+ * dtype_bytes: 4 (_f32), 8 (_f64), 2 (_bf16). */
+size_t bxr_attn_bwd_workspace_bytes(int dtype_bytes, int B, int S, int H, int D, unsigned flags);
+
+#define BXR_DECLARE_OPS(SUF, TV, TW)                                                                         \
+    /* box_attn_forward  (box_attn.cu:15-71): out[b,q,h,:] = sum_l sum_p attn * bilinear(value_l, loc) */   \
+    int bxr_box_attn_fwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,           \
+                               const TW* loc, const TW* attn,                                                \
+                               int B, int S, int H, int D, int L, int Nq, int P,                             \
+                               TV* out, unsigned flags, bxr_stream_t stream);                                \
+    /* box_attn_backward (box_attn.cu:74-135) */                                                            \
+    int bxr_box_attn_bwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,           \
+                               const TW* loc, const TW* attn, const TV* grad_out,                            \
+                               int B, int S, int H, int D, int L, int Nq, int P,                             \
+                               TV* grad_value, TW* grad_loc, TW* grad_attn,                                  \
+                               void* workspace, size_t workspace_bytes, unsigned flags, bxr_stream_t stream); \
+    /* instance_attn_forward (instance_attn.cu:15-82): out as above with spatial_w;                          \
+       mask_out[b,q,p,h,:] = sum_l level_w * bilinear */                                                     \
+    int bxr_instance_attn_fwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,      \
+                                    const TW* loc, const TW* spatial_w, const TW* level_w,                   \
+                                    int B, int S, int H, int D, int L, int Nq, int P,                        \
+                                    TV* out, TV* mask_out, unsigned flags, bxr_stream_t stream);             \
+    /* instance_attn_backward (instance_attn.cu:85-157) */                                                   \
+    int bxr_instance_attn_bwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,      \
+                                    const TW* loc, const TW* spatial_w, const TW* level_w,                   \
+                                    const TV* grad_out, const TV* grad_mask,                                 \
+                                    int B, int S, int H, int D, int L, int Nq, int P,                        \
+                                    TV* grad_value, TW* grad_loc, TW* grad_spatial_w, TW* grad_level_w,      \
+                                    void* workspace, size_t workspace_bytes, unsigned flags,                 \
+                                    bxr_stream_t stream);
+
+BXR_DECLARE_OPS(f32, float, float)
+BXR_DECLARE_OPS(f64, double, double)
+BXR_DECLARE_OPS(bf16, bxr_bf16, float)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOXATTN_B200_H_ */
