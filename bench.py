@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- box-attn fwd+bwd Gsamples/s at the COCO 4-level encoder config (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variants]
+
+A *step* is one forward + one backward pass of the box-attention op over one batch of synthetic
+multi-scale feature maps (BASELINE.json configs[1]: 4 FPN levels of a 1333x800 image, C=256,
+8 heads, Nq = S = 22 223 encoder queries, 4x4 grid, fp32, B=1 image per GPU).  A *sample* is
+one bilinear sample point for one (image, query, head, level, point): N = B*Nq*H*L*P per pass.
+
+Printed (rank 0, ONE JSON line on stdout):
+  value      whole-job Gsamples/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API (BoxAttnFunction.apply + backward) with HOST
+             (pinned) inputs: H2D of value/loc/weights/grad_out and D2H of out + all gradients
+             inside the timed region
+  roofline   dominant kernel (backward) : algorithmic bytes / its CUDA-event time
+             vs the measured HBM copy bandwidth of MEASURED_PEAKS.json; roofline_fwd likewise
+  cpu_baseline  the reference's pure-PyTorch grid_sample formulation (oracle/plain.py) on the
+             host CPU, all threads, on a bounded sample of the same workload
+
+--impl reference times that CPU formulation as the "reference arm": the reference has no CPU op
+(box_attn.h:53) and its CUDA extension cannot be installed offline against torch 2.11, so its own
+test oracle (tests/box_attn_test.py:9-42), restated in oracle/plain.py, is the CPU implementation.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "box-attn fwd+bwd Gsamples/s @ COCO 4-level"
+UNIT = "Gsamples/s"
+CFG = dict(workload="BoxeR-2D encoder box-attn: 4 FPN levels (100x167,50x84,25x42,13x21) of 1333x800, C=256, "
+                    "Nq=S=22223, 8 heads, 4x4 grid, fp32, fwd+bwd",
+           B_per_gpu=1, K=4, heads=8, head_dim=32, levels=4, Nq=22223, dist="box")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ our arm
+def make_sets(dev, n_sets, seed0, K=4, dist="box", B=1):
+    from boxer_b200 import workloads as W
+    sets = []
+    for i in range(n_sets):
+        w = W.coco_encoder(B=B, K=K, dist=dist, device=dev, seed=seed0 + i)
+        go = torch.randn(B, w.value.shape[1], w.value.shape[2] * w.value.shape[3], device=dev)
+        sets.append((w, go))
+    return sets
+
+
+def step_resident(ops, w, go):
+    """fwd + bwd straight through the tensor-level API (= what autograd calls), device-resident inputs."""
+    out = ops.box_attn_forward(w.value, w.shapes, w.level_start, w.loc, w.weights[0], 64)
+    n = ops.last_launch_count()
+    grads = ops.box_attn_backward(w.value, w.shapes, w.level_start, w.loc, w.weights[0], go, 64)
+    return out, grads, n + ops.last_launch_count()
+
+
+def timed(fn, steps, warmup, dist_on):
+    """W warm-up steps, then exactly K steps between barrier+synchronize pairs, CUDA events; max over ranks."""
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def kernel_times(ops, sets, reps):
+    """Average CUDA-event duration of the forward call and of the backward call (memset + kernel)."""
+    f_ms, b_ms = [], []
+    for i in range(reps):
+        w, go = sets[i % len(sets)]
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        ops.box_attn_forward(w.value, w.shapes, w.level_start, w.loc, w.weights[0], 64)
+        b.record()
+        ops.box_attn_backward(w.value, w.shapes, w.level_start, w.loc, w.weights[0], go, 64)
+        c.record()
+        torch.cuda.synchronize()
+        f_ms.append(a.elapsed_time(b))
+        b_ms.append(b.elapsed_time(c))
+    return statistics.mean(f_ms), statistics.mean(b_ms)
+
+
+def e2e_run(sets, steps, warmup, dist_on):
+    """Public API with host buffers: pinned host tensors -> H2D -> BoxAttnFunction fwd+bwd -> D2H of out and grads."""
+    import boxer_b200
+    dev = sets[0][0].value.device
+    host = []
+    for w, go in sets:
+        host.append(tuple(t.detach().cpu().pin_memory() for t in (w.value, w.loc, w.weights[0], go)))
+    w0 = sets[0][0]
+    res_host = [torch.empty_like(t, device="cpu").pin_memory()
+                for t in (sets[0][1], w0.value, w0.loc, w0.weights[0])]      # out, gV, gLoc, gW
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = sum(t.numel() * t.element_size() for t in res_host)
+
+    def fn(i):
+        hv, hl, ha, hg = host[i % len(host)]
+        v = hv.to(dev, non_blocking=True).requires_grad_(True)
+        l = hl.to(dev, non_blocking=True).requires_grad_(True)
+        a = ha.to(dev, non_blocking=True).requires_grad_(True)
+        g = hg.to(dev, non_blocking=True)
+        out = boxer_b200.BoxAttnFunction.apply(v, w0.shapes, w0.level_start, l, a, 64)
+        out.backward(g)
+        res_host[0].copy_(out.detach(), non_blocking=True)
+        res_host[1].copy_(v.grad, non_blocking=True)
+        res_host[2].copy_(l.grad, non_blocking=True)
+        res_host[3].copy_(a.grad, non_blocking=True)
+
+    ms = timed(fn, steps, warmup, dist_on)
+    return ms, h2d, d2h
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_pass(cpu_w, go, frac=1.0):
+    """One fwd+bwd of the reference's grid_sample formulation on the host CPU; returns (seconds, samples)."""
+    from oracle import plain
+    value, loc, attn = cpu_w.value, cpu_w.loc, cpu_w.weights[0]
+    nq = max(1, int(round(loc.shape[1] * frac)))
+    value = value.clone().requires_grad_(True)
+    loc = loc[:, :nq].clone().requires_grad_(True)
+    attn = attn[:, :nq].clone().requires_grad_(True)
+    g = go[:, :nq]
+    B, S = value.shape[:2]
+    t0 = time.perf_counter()
+    out = plain.plain_box_attn(value.view(B, S, -1), cpu_w.shapes, 2 * loc - 1, attn)
+    out.backward(g)
+    dt = time.perf_counter() - t0
+    n = B * nq * loc.shape[2] * loc.shape[3] * loc.shape[4]
+    return dt, n
+
+
+def cpu_workload(K=4):
+    from boxer_b200 import workloads as W
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = W.coco_encoder(B=1, K=K, dist="box", device="cpu", seed=3)
+    go = torch.randn(1, w.value.shape[1], 256)
+    return w, go
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    w, go = cpu_workload(CFG["K"])
+    total = args.steps + args.warmup
+    frac = min(1.0, 24.0 / max(1, total))      # keep the whole run within a few minutes of CPU time
+    for _ in range(args.warmup):
+        cpu_pass(w, go, frac)
+    t, n = 0.0, 0
+    for _ in range(args.steps):
+        dt, ns = cpu_pass(w, go, frac)
+        t += dt
+        n += ns
+    val = n / t / 1e9
+    cores = torch.get_num_threads()
+    sample = (f"each step = fwd+bwd of the grid_sample formulation over the first {frac:.3f} of the {CFG['Nq']} queries "
+              f"(all 4 levels, K=4, fp32), {args.steps} steps, {cpu_model()}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(CFG, query_fraction=frac),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------ main
+def variants(ops, dev, bw_peak):
+    """Extra measurements (stderr + gpurun_out/variants.json); not part of the contract line."""
+    from boxer_b200 import workloads as W
+    res = {}
+
+    def time_call(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    for K in (2, 4):
+        for dist in ("box", "uniform"):
+            for dt in (torch.float32, torch.bfloat16):
+                w = W.coco_encoder(K=K, dist=dist, device=dev)
+                v = w.value.to(dt)
+                go = torch.randn(1, v.shape[1], 256, device=dev, dtype=dt)
+                a = w.weights[0]
+                tf = time_call(lambda: ops.box_attn_forward(v, w.shapes, w.level_start, w.loc, a, 64))
+                tb = time_call(lambda: ops.box_attn_backward(v, w.shapes, w.level_start, w.loc, a, go, 64))
+                n = w.n_samples
+                sz = v.element_size()
+                bf = W.bytes_per_sample(False, False, 32, 4, K * K, sz)
+                bb = W.bytes_per_sample(False, True, 32, 4, K * K, sz)
+                res[f"enc_K{K}_{dist}_{'f32' if dt == torch.float32 else 'bf16'}"] = {
+                    "fwd_ms": tf, "bwd_ms": tb, "fwd_Gs": n / tf / 1e6, "fwdbwd_Gs": n / (tf + tb) / 1e6,
+                    "fwd_frac": n * bf / (tf * 1e-3) / 1e9 / bw_peak, "bwd_frac": n * bb / (tb * 1e-3) / 1e9 / bw_peak}
+    for K in (14, 28):
+        for dt in (torch.float32, torch.bfloat16):
+            m = W.coco_mask_head(K=K, device=dev)
+            v = m.value.to(dt)
+            go = torch.randn(1, 300, 256, device=dev, dtype=dt)
+            gm = torch.randn(1, 300, K * K, 256, device=dev, dtype=dt)
+            sw, lw = m.weights
+            tf = time_call(lambda: ops.instance_attn_forward(v, m.shapes, m.level_start, m.loc, sw, lw, 64))
+            tb = time_call(lambda: ops.instance_attn_backward(v, m.shapes, m.level_start, m.loc, sw, lw, go, gm, 64))
+            n = m.n_samples
+            sz = v.element_size()
+            bf = W.bytes_per_sample(True, False, 32, 4, K * K, sz)
+            bb = W.bytes_per_sample(True, True, 32, 4, K * K, sz)
+            res[f"mask_K{K}_{'f32' if dt == torch.float32 else 'bf16'}"] = {
+                "fwd_ms": tf, "bwd_ms": tb, "fwd_Gs": n / tf / 1e6, "fwdbwd_Gs": n / (tf + tb) / 1e6,
+                "fwd_frac": n * bf / (tf * 1e-3) / 1e9 / bw_peak, "bwd_frac": n * bb / (tb * 1e-3) / 1e9 / bw_peak}
+    r = W.bev_rotated(B=8, device=dev)
+    go = torch.randn(8, 1000, 128, device=dev)
+    tf = time_call(lambda: ops.box_attn_forward(r.value, r.shapes, r.level_start, r.loc, r.weights[0], 64))
+    tb = time_call(lambda: ops.box_attn_backward(r.value, r.shapes, r.level_start, r.loc, r.weights[0], go, 64))
+    res["bev_B8"] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_Gs": r.n_samples / tf / 1e6, "fwdbwd_Gs": r.n_samples / (tf + tb) / 1e6}
+    w = W.coco_encoder(K=4, dist="box", device=dev)
+    go = torch.randn(1, w.value.shape[1], 256, device=dev)
+    ops.set_deterministic(True)
+    tb = time_call(lambda: ops.box_attn_backward(w.value, w.shapes, w.level_start, w.loc, w.weights[0], go, 64), reps=5)
+    ops.set_deterministic(None)
+    res["enc_K4_box_f32_deterministic"] = {"bwd_ms": tb}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variants", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    import boxer_b200
+    from boxer_b200 import ops
+    from boxer_b200 import workloads as W
+
+    bw_peak, peak_src = peaks()
+    sets = make_sets(dev, 2, seed0=3 + 10 * rank, K=CFG["K"], dist=CFG["dist"], B=CFG["B_per_gpu"])
+    n_samples = sets[0][0].n_samples
+    launches = [0]
+
+    def fn(i):
+        w, go = sets[i % len(sets)]
+        _, _, n = step_resident(ops, w, go)
+        launches[0] += n
+
+    for i in range(3):
+        fn(i)
+    launches[0] = 0
+    with ClockSampler(local_rank) as clk:
+        ms = timed(fn, args.steps, args.warmup, dist_on)
+        kf_ms, kb_ms = kernel_times(ops, sets, max(10, min(args.steps, 50)))
+    n_launch = launches[0] - 2 * args.warmup      # kernels inside the timed region
+    clocks = clk.summary()
+    value = n_gpus * n_samples * args.steps / (ms * 1e-3) / 1e9
+
+    ms_e2e, h2d, d2h = e2e_run(sets, max(3, min(args.steps, 20)), 3, dist_on)
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_val = n_gpus * n_samples * e2e_steps / (ms_e2e * 1e-3) / 1e9
+
+    d = sets[0][0].dims
+    bf = W.bytes_per_sample(False, False, d["D"], d["L"], d["P"], 4)
+    bb = W.bytes_per_sample(False, True, d["D"], d["L"], d["P"], 4)
+    ach_f = n_samples * bf / (kf_ms * 1e-3) / 1e9
+    ach_b = n_samples * bb / (kb_ms * 1e-3) / 1e9
+    ach_s = n_samples * (bf + bb) / ((kf_ms + kb_ms) * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": dict(CFG, n_samples_per_gpu_step=n_samples,
+                       l2="working set ~364 MB/step (> 126 MB L2); 2 rotating input sets; no explicit flush",
+                       locations="box-structured (encoder reference windows + init-state offsets), see boxer_b200/workloads.py"),
+        "roofline": {"bound": "hbm", "kernel": "attn_bwd_vec_kernel<float,8,box,atomic> (+ grad_value memset)",
+                     "achieved": ach_b, "peak": bw_peak, "unit": "GB/s", "frac": ach_b / bw_peak, "traffic": None,
+                     "peak_source": peak_src, "bytes_per_sample": bb, "ms_per_launch": kb_ms},
+        "roofline_fwd": {"bound": "hbm", "kernel": "attn_fwd_vec_kernel<float,8,box,U=4>", "achieved": ach_f, "peak": bw_peak,
+                         "unit": "GB/s", "frac": ach_f / bw_peak, "traffic": None, "bytes_per_sample": bf,
+                         "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6},
+        "roofline_step": {"achieved": ach_s, "frac": ach_s / bw_peak, "unit": "GB/s"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                "path": "pinned host -> H2D -> BoxAttnFunction.apply + backward -> D2H(out, grad_value, grad_loc, grad_attn)"},
+        "gpu_launches": n_launch,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cw, cgo = cpu_workload(CFG["K"])
+        cpu_pass(cw, cgo, 0.25)                      # warm-up on a quarter of the queries
+        runs = [cpu_pass(cw, cgo, 1.0) for _ in range(3)]
+        t = statistics.median(r[0] for r in runs)
+        line["cpu_baseline"] = {
+            "value": runs[0][1] / t / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"full config (all {CFG['Nq']} queries, K=4, fp32) fwd+bwd of the grid_sample formulation "
+                      f"(oracle/plain.py), median of 3 after warm-up, {t * 1e3:.0f} ms/pass, {cpu_model()}"}
+
+    if args.variants and rank == 0:
+        v = variants(ops, dev, bw_peak)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "variants.json"), "w") as f:
+            json.dump(v, f, indent=1)
+        for k, r in v.items():
+            print(k, {a: round(b, 4) for a, b in r.items()}, file=sys.stderr)
+
+    if rank == 0:
+        print(json.dumps(line))
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

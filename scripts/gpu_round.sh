@@ -1,0 +1,26 @@
+#!/bin/bash
+# One gpurun call: GPU tests, bench (+variants), ncu launch list, ncu full captures of the two hot kernels.
+# usage: gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh <tag> [quick]'
+TAG=${1:-r01}
+MODE=${2:-full}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv > $OUT/gpu.csv 2>&1
+nproc > $OUT/host.txt; grep -m1 "model name" /proc/cpuinfo >> $OUT/host.txt
+python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log
+tail -5 $OUT/pytest.log
+timeout 600 python bench.py --variants > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+cat $OUT/bench.json; tail -30 $OUT/bench.err
+cp gpurun_out/variants.json $OUT/variants.json 2>/dev/null
+if [ "$MODE" != "quick" ]; then
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_fwd_vec -s 2 -c 1 -f -o $OUT/fwd_enc_K4 \
+    python scripts/prof_driver.py --workload enc --K 4 > $OUT/ncu_fwd.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_vec -s 2 -c 1 -f -o $OUT/bwd_enc_K4 \
+    python scripts/prof_driver.py --workload enc --K 4 > $OUT/ncu_bwd.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_fwd_vec -s 2 -c 1 -f -o $OUT/fwd_enc_K4_uniform \
+    python scripts/prof_driver.py --workload enc --K 4 --dist uniform > $OUT/ncu_fwd_u.log 2>&1
+fi
+ls -la $OUT

@@ -79,13 +79,18 @@ def _close(got, want, tol, what):
 
 
 # ============================================================== golden fixtures (reference outputs)
+def _gold_tol(inp, dtype):
+    # the reference's check_forward("float") case was itself computed in fp32
+    return max(TOL[dtype], 2e-6) if inp["value"].dtype == torch.float32 else TOL[dtype]
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16], ids=["f64", "f32", "bf16"])
 @pytest.mark.parametrize("case", list(helpers.box_inputs()))
 def test_box_golden(case, dtype):
     inp, gold = helpers.box_inputs()[case], helpers.golden("box_attn_golden")[case]
     go = gold.get("grad_out")
     out, grads = _run_box(inp, dtype, go)
-    tol = TOL[dtype]
+    tol = _gold_tol(inp, dtype)
     assert out.dtype == dtype and out.shape == gold["out"].shape
     _close(out, gold["out"], tol, "out")
     if dtype == torch.float32:   # the reference-scale inputs: absolute bar as BASELINE.md states it
@@ -113,7 +118,7 @@ def test_instance_golden(case, dtype):
     inp, gold = helpers.instance_inputs()[case], helpers.golden("instance_attn_golden")[case]
     go, gm = _inst_grads_in(inp, gold)
     out, mask, grads = _run_inst(inp, dtype, go, gm)
-    tol = TOL[dtype]
+    tol = _gold_tol(inp, dtype)
     assert mask.shape == gold["mask_out"].shape
     _close(out, gold["out"], tol, "out")
     _close(mask, gold["mask_out"], tol, "mask_out")
