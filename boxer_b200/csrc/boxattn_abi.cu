@@ -9,6 +9,7 @@
 #include <type_traits>
 
 #include "boxattn_kernels.cuh"
+#include "boxattn_window.cuh"
 #include "../../include/boxattn_b200.h"
 
 namespace {
@@ -155,6 +156,54 @@ int dispatch_bwd_vec(int g, AttnParams& p, cudaStream_t st) {
     BXR_DISPATCH_G(g, (bwd_vec<TV, INSTANCE, ACC, G>(p, st)))
 }
 
+// ---- footprint-window kernels (boxattn_window.cuh): box op, enough rows to fill the GPU, P <= 4*G
+bool use_window(const AttnParams& p, int g, unsigned flags) {
+    if (flags & BXR_FLAG_PATH_POINT) return false;
+    if (g != 4 && g != 8 && g != 16) return false;
+    if (p.P > 4 * g || p.P < 1) return false;
+    if (flags & BXR_FLAG_PATH_WINDOW) return true;
+    const long long groups = kThreads / g;
+    return p.rows >= 2LL * sm_count() * groups;     // small (decoder-sized) calls keep the point-split kernels
+}
+
+template <typename TV, int G, int PPL>
+int fwd_win(AttnParams& p, cudaStream_t st) {
+    p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
+    return launch_units<box_fwd_win_kernel<TV, G, PPL>>(p, st, "box_fwd_win_kernel");
+}
+template <typename TV, int G, int PPL, typename ACC>
+int bwd_win(AttnParams& p, cudaStream_t st) {
+    p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
+    return launch_units<box_bwd_win_kernel<TV, G, PPL, ACC>>(p, st, "box_bwd_win_kernel");
+}
+
+#define BXR_DISPATCH_WIN(G_, PPL_, CALL)                                                      \
+    switch ((G_) * 8 + (PPL_)) {                                                              \
+        case 4 * 8 + 1: { constexpr int G = 4, PPL = 1; return CALL; }                        \
+        case 4 * 8 + 2: { constexpr int G = 4, PPL = 2; return CALL; }                        \
+        case 4 * 8 + 4: { constexpr int G = 4, PPL = 4; return CALL; }                        \
+        case 8 * 8 + 1: { constexpr int G = 8, PPL = 1; return CALL; }                        \
+        case 8 * 8 + 2: { constexpr int G = 8, PPL = 2; return CALL; }                        \
+        case 8 * 8 + 4: { constexpr int G = 8, PPL = 4; return CALL; }                        \
+        case 16 * 8 + 1: { constexpr int G = 16, PPL = 1; return CALL; }                      \
+        case 16 * 8 + 2: { constexpr int G = 16, PPL = 2; return CALL; }                      \
+        default: { constexpr int G = 16, PPL = 4; return CALL; }                              \
+    }
+
+int ppl_of(int P, int g) {
+    const int n = (P + g - 1) / g;
+    return n <= 1 ? 1 : (n <= 2 ? 2 : 4);
+}
+
+template <typename TV>
+int dispatch_fwd_win(int g, AttnParams& p, cudaStream_t st) {
+    BXR_DISPATCH_WIN(g, ppl_of(p.P, g), (fwd_win<TV, G, PPL>(p, st)))
+}
+template <typename TV, typename ACC>
+int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st) {
+    BXR_DISPATCH_WIN(g, ppl_of(p.P, g), (bwd_win<TV, G, PPL, ACC>(p, st)))
+}
+
 void fill_sizes(AttnParams& p, int B, int S, int H, int D, int L, int Nq, int P) {
     p.B = B; p.S = S; p.H = H; p.D = D; p.L = L; p.Nq = Nq; p.P = P;
     p.LP = L * P;
@@ -170,7 +219,6 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
             int B, int S, int H, int D, int L, int Nq, int P, TV* out, TV* mask_out, unsigned flags, bxr_stream_t stream) {
     g_launches = 0;
     g_detail[0] = 0;
-    (void)flags;
     if (int s = check_dims(B, S, H, D, L, Nq, P)) return s;
     AttnParams p;
     memset(&p, 0, sizeof(p));
@@ -190,7 +238,12 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
 
     const int g = vec_group<TV>(D, p.LP);
     if (g && aligned16(value) && aligned16(out) && (!INSTANCE || aligned16(mask_out)) && aligned8(loc)) {
-        if constexpr (!std::is_same<TV, double>::value) return dispatch_fwd_vec<TV, INSTANCE>(g, p, st);
+        if constexpr (!std::is_same<TV, double>::value) {
+            if constexpr (!INSTANCE) {
+                if (use_window(p, g, flags)) return dispatch_fwd_win<TV>(g, p, st);
+            }
+            return dispatch_fwd_vec<TV, INSTANCE>(g, p, st);
+        }
     }
     return launch_rows<attn_fwd_gen_kernel<TV, INSTANCE>>(p, st, "attn_fwd_gen_kernel");
 }
@@ -294,7 +347,12 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
     const bool vec_ok = g && aligned16(value) && aligned16(grad_out) && aligned16(acc) && (!INSTANCE || aligned16(grad_mask)) &&
                         aligned8(loc) && aligned8(grad_loc);
     if constexpr (!std::is_same<TV, double>::value) {
-        if (vec_ok) {
+        bool win = false;
+        if constexpr (!INSTANCE) win = vec_ok && use_window(p, g, flags);
+        if (win) {
+            if constexpr (!INSTANCE)
+                status = det ? dispatch_bwd_win<TV, long long>(g, p, st) : dispatch_bwd_win<TV, float>(g, p, st);
+        } else if (vec_ok) {
             status = det ? dispatch_bwd_vec<TV, INSTANCE, long long>(g, p, st) : dispatch_bwd_vec<TV, INSTANCE, float>(g, p, st);
         } else {
             status = det ? launch_rows<attn_bwd_gen_kernel<TV, INSTANCE, long long>>(p, st, "attn_bwd_gen_kernel")

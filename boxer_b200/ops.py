@@ -31,6 +31,10 @@ from . import _native
 _DET_OVERRIDE = None          # None: follow torch.are_deterministic_algorithms_enabled()
 FLAG_DETERMINISTIC = 0x1
 
+FLAG_PATH_WINDOW = 0x2
+FLAG_PATH_POINT = 0x4
+_PATH_FLAGS = 0               # tuning / testing override of the kernel family (see set_kernel_path)
+
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
 
 
@@ -45,6 +49,13 @@ def deterministic() -> bool:
     if _DET_OVERRIDE is not None:
         return bool(_DET_OVERRIDE)
     return torch.are_deterministic_algorithms_enabled()
+
+
+def set_kernel_path(path: str = "auto"):
+    """"auto" (default): footprint-window kernels for large box-attention calls, point kernels otherwise;
+    "window" / "point": force one family where it applies (A/B benchmarking and tests)."""
+    global _PATH_FLAGS
+    _PATH_FLAGS = {"auto": 0, "window": FLAG_PATH_WINDOW, "point": FLAG_PATH_POINT}[path]
 
 
 def last_launch_count() -> int:
@@ -134,7 +145,7 @@ def box_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, att
         st = getattr(lib, f"bxr_box_attn_fwd_{suf}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), B, S, H, D, L, Nq, P,
-            out.data_ptr(), 0, _stream(value.device))
+            out.data_ptr(), _PATH_FLAGS, _stream(value.device))
     _native.check(st, "box_attn_forward")
     return out
 
@@ -147,7 +158,7 @@ def box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, at
         raise RuntimeError("grad_output must match the forward output's dtype and size")
     _step_check(B, im2col_step)
     lib = _native.load()
-    flags = FLAG_DETERMINISTIC if deterministic() else 0
+    flags = (FLAG_DETERMINISTIC if deterministic() else 0) | _PATH_FLAGS
     grad_value = torch.empty_like(value)
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)

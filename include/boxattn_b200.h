@@ -67,6 +67,10 @@ typedef enum bxr_status {
 #define BXR_FLAG_DETERMINISTIC 0x1u /* backward: order-independent (bit-reproducible) grad_value scatter via
                                        64-bit fixed-point accumulation instead of floating-point atomics */
 
+#define BXR_FLAG_PATH_WINDOW 0x2u   /* tuning/testing: use the footprint-window kernels whenever they apply,
+                                       even for row counts where the point-split kernels are the default */
+#define BXR_FLAG_PATH_POINT 0x4u    /* tuning/testing: never use the footprint-window kernels */
+
 typedef void* bxr_stream_t;   /* a cudaStream_t */
 typedef uint16_t bxr_bf16;    /* raw bfloat16 bits */
 
