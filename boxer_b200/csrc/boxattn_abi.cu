@@ -162,6 +162,7 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
     if (g != 4 && g != 8 && g != 16) return false;
     if (p.P > 4 * g || p.P < 1) return false;
     if (flags & BXR_FLAG_PATH_WINDOW) return true;
+    if (p.P < 8) return false;                      // 2x2 grids: too few points per level to amortise the window
     const long long groups = kThreads / g;
     return p.rows >= 2LL * sm_count() * groups;     // small (decoder-sized) calls keep the point-split kernels
 }

@@ -30,6 +30,20 @@ namespace bxr {
 
 constexpr int kWinSide = 8;
 constexpr int kWinSlots = kWinSide * kWinSide;
+// per-group pitch of a window in 32-bit words: 64 slots + 4 words of skew, so that the 16-byte
+// row reads of the 4 (G=8) or 8 (G=4) groups of a warp fall into different banks
+constexpr int kWinPitch = kWinSlots + 4;
+
+// Pixel weights are accumulated in the shared-memory window as 32-bit fixed point with a per
+// (row, level) power-of-two scale: integer atomics are single instructions (a float atomicAdd on
+// shared memory is a compare-and-swap loop on sm_100) and the sum is order independent.
+// With S = sum_p |attn_p| <= 2^e every pixel weight is bounded by S, so scale = 2^(30-e) cannot
+// overflow; the rounding step is 2^-31 of S, below fp32 resolution of the largest weight.
+__device__ __forceinline__ int fixed_scale_exp(float S) {
+    const int e = ((__float_as_int(S) >> 23) & 0xff) - 126;     // S < 2^e  (normal S)
+    return max(-126, min(126, 30 - e));
+}
+__device__ __forceinline__ float pow2f(int k) { return __int_as_float((127 + k) << 23); }
 
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
@@ -86,18 +100,18 @@ __device__ __forceinline__ LanePoint lane_point(const float* __restrict__ loc_l,
 // ------------------------------------------------------------------------------------------------
 // Forward.  One group of G lanes per row; grid-stride over contiguous blocks of rows.
 template <typename TV, int G, int PPL>
-__global__ void __launch_bounds__(kThreads) box_fwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
     constexpr int GROUPS = kThreads / G;
     __shared__ LevelTable lv;
-    __shared__ __align__(16) float s_win[GROUPS][kWinSlots];
+    __shared__ __align__(16) int s_win[GROUPS * kWinPitch];
     load_levels(lv, p);
 
     const int lane = threadIdx.x % G;
     const int gid = threadIdx.x / G;
     const unsigned gm = group_mask<G>();
-    float* win = s_win[gid];
+    int* win = s_win + gid * kWinPitch;
     const int HD = p.H * p.D;
     const TV* __restrict__ value = static_cast<const TV*>(p.value);
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -124,48 +138,59 @@ __global__ void __launch_bounds__(kThreads) box_fwd_win_kernel(const AttnParams 
             // ---- A: own points, touched pixel range
             LanePoint pt[PPL];
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
+            float S = 0.f;
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
                 pt[k] = lane_point(loc_row + l * p.P * 2, w_row + l * p.P, lane + k * G, p.P, lh, lw);
                 if (pt[k].inside) {
                     bx0 = min(bx0, pt[k].x0); bx1 = max(bx1, pt[k].x0 + 1);
                     by0 = min(by0, pt[k].y0); by1 = max(by1, pt[k].y0 + 1);
+                    S += fabsf(pt[k].aw);
                 }
             }
             const int X0 = max(gmin<G>(bx0, gm), 0), X1 = min(gmax<G>(bx1, gm), lw - 1);
             const int Y0 = max(gmin<G>(by0, gm), 0), Y1 = min(gmax<G>(by1, gm), lh - 1);
             const int nx = X1 - X0 + 1, ny = Y1 - Y0 + 1;
             if (nx <= 0 || ny <= 0) continue;   // no point of this level passed the window test
+            S = gsum<G>(S, gm);
+            if (S == 0.f) continue;             // every weight of this level is exactly zero
 
-            if (nx <= kWinSide && ny <= kWinSide) {
-                // ---- B: scatter pixel weights into the window
-                for (int s = lane; s < ny * kWinSide; s += G) win[s] = 0.f;
+            // non-finite weights (S is NaN/inf) take the float path below so that they propagate
+            if (nx <= kWinSide && ny <= kWinSide && S <= 3.0e38f) {
+                // ---- B: scatter pixel weights into the window (32-bit fixed point, see fixed_scale_exp)
+                const int ke = fixed_scale_exp(S);
+                const float scale = pow2f(ke), inv_scale = pow2f(-ke);
+                for (int s = lane; s < ny * kWinSide; s += G) win[s] = 0;
                 __syncwarp(gm);
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     if (pt[k].inside) {
                         const int sx = pt[k].x0 - X0, sy = pt[k].y0 - Y0;   // -1 .. n-1
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
+                        const float a = pt[k].aw * scale;
                         const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
-                        float* wp = win + sy * kWinSide + sx;
-                        if (vy0 && vx0) atomicAdd(wp, hy * hx * pt[k].aw);
-                        if (vy0 && vx1) atomicAdd(wp + 1, hy * pt[k].lx * pt[k].aw);
-                        if (vy1 && vx0) atomicAdd(wp + kWinSide, pt[k].ly * hx * pt[k].aw);
-                        if (vy1 && vx1) atomicAdd(wp + kWinSide + 1, pt[k].ly * pt[k].lx * pt[k].aw);
+                        int* wp = win + sy * kWinSide + sx;
+                        if (vy0 && vx0) atomicAdd(wp, __float2int_rn(hy * hx * a));
+                        if (vy0 && vx1) atomicAdd(wp + 1, __float2int_rn(hy * pt[k].lx * a));
+                        if (vy1 && vx0) atomicAdd(wp + kWinSide, __float2int_rn(pt[k].ly * hx * a));
+                        if (vy1 && vx1) atomicAdd(wp + kWinSide + 1, __float2int_rn(pt[k].ly * pt[k].lx * a));
                     }
                 }
                 __syncwarp(gm);
                 // ---- C: one row load per unique pixel
                 const TV* wbase = vlev + ((long long)Y0 * lw + X0) * HD;
                 for (int iy = 0; iy < ny; ++iy) {
-                    const float4 wa = *reinterpret_cast<const float4*>(win + iy * kWinSide);
-                    const float4 wb = *reinterpret_cast<const float4*>(win + iy * kWinSide + 4);
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    const int4 wa = *reinterpret_cast<const int4*>(win + iy * kWinSide);
+                    const int4 wb = *reinterpret_cast<const int4*>(win + iy * kWinSide + 4);
+                    const int wi[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    float wv[8];
+#pragma unroll
+                    for (int ix = 0; ix < 8; ++ix) wv[ix] = (float)wi[ix] * inv_scale;
                     const TV* rbase = wbase + (long long)iy * lw * HD;
                     float v[8][VEC];
 #pragma unroll
                     for (int ix = 0; ix < 8; ++ix) {
-                        if (ix < nx && wv[ix] != 0.f) {
+                        if (ix < nx && wi[ix] != 0) {
                             V::load(rbase + ix * HD, v[ix]);
                         } else {
 #pragma unroll
@@ -230,22 +255,48 @@ __device__ __forceinline__ void scatter_row(ACC* dst, const float (&g)[VEC], flo
     }
 }
 
+// Sum 4 per-lane partials over the G lanes of a group with a transpose reduction (4 shuffles for
+// G = 8 instead of 12): afterwards every lane holds the full sum of ONE of the four values;
+// returns its index.  Lanes that hold the same index hold the same total.
+template <int G>
+__device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, unsigned gm) {
+    static_assert(G == 4 || G == 8 || G == 16, "window kernels are built for G in {4, 8, 16}");
+    if (G == 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] += __shfl_xor_sync(gm, d[i], 8);
+    }
+    constexpr int HI = (G == 4) ? 2 : 4;      // lane bit that picks the pair {0,1} or {2,3}
+    constexpr int LO = HI / 2;                // lane bit that picks within the pair
+    const bool hi = (lane & HI) != 0;
+    float a = hi ? d[2] : d[0], b = hi ? d[3] : d[1];
+    const float sa = hi ? d[0] : d[2], sb = hi ? d[1] : d[3];
+    a += __shfl_xor_sync(gm, sa, HI);
+    b += __shfl_xor_sync(gm, sb, HI);
+    const bool lo = (lane & LO) != 0;
+    float r = lo ? b : a;
+    const float sr = lo ? a : b;
+    r += __shfl_xor_sync(gm, sr, LO);
+    if (G >= 8) r += __shfl_xor_sync(gm, r, 1);
+    total = r;
+    return (hi ? 2 : 0) + (lo ? 1 : 0);
+}
+
 template <typename TV, int G, int PPL, typename ACC>
-__global__ void __launch_bounds__(kThreads) box_bwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
     constexpr int GROUPS = kThreads / G;
     constexpr bool DET = sizeof(ACC) == 8;
     __shared__ LevelTable lv;
-    __shared__ __align__(16) float s_win[GROUPS][kWinSlots];   // pixel weights  W[pix]
-    __shared__ __align__(16) float s_dot[GROUPS][kWinSlots];   // d[pix] = <grad_out, value[pix]>
+    __shared__ __align__(16) int s_win[GROUPS * kWinPitch];     // pixel weights W[pix], fixed point
+    __shared__ __align__(16) float s_dot[GROUPS * kWinPitch];   // "touched" flag, then d[pix] = <grad_out, value[pix]>
     load_levels(lv, p);
 
     const int lane = threadIdx.x % G;
     const int gid = threadIdx.x / G;
     const unsigned gm = group_mask<G>();
-    float* win = s_win[gid];
-    float* dot = s_dot[gid];
+    int* win = s_win + gid * kWinPitch;
+    float* dot = s_dot + gid * kWinPitch;
     const int HD = p.H * p.D;
     const TV* __restrict__ value = static_cast<const TV*>(p.value);
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -275,6 +326,7 @@ __global__ void __launch_bounds__(kThreads) box_bwd_win_kernel(const AttnParams 
             LanePoint pt[PPL];
             float g_a[PPL], g_x[PPL], g_y[PPL];     // this lane's results for its own points
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
+            float S = 0.f;
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
                 pt[k] = lane_point(loc_row + l * p.P * 2, w_row + l * p.P, lane + k * G, p.P, lh, lw);
@@ -282,67 +334,71 @@ __global__ void __launch_bounds__(kThreads) box_bwd_win_kernel(const AttnParams 
                 if (pt[k].inside) {
                     bx0 = min(bx0, pt[k].x0); bx1 = max(bx1, pt[k].x0 + 1);
                     by0 = min(by0, pt[k].y0); by1 = max(by1, pt[k].y0 + 1);
+                    S += fabsf(pt[k].aw);
                 }
             }
             const int X0 = max(gmin<G>(bx0, gm), 0), X1 = min(gmax<G>(bx1, gm), lw - 1);
             const int Y0 = max(gmin<G>(by0, gm), 0), Y1 = min(gmax<G>(by1, gm), lh - 1);
             const int nx = X1 - X0 + 1, ny = Y1 - Y0 + 1;
+            S = gsum<G>(S, gm);
 
-            if (nx > 0 && ny > 0 && nx <= kWinSide && ny <= kWinSide) {
-                // B: pixel weights.  The d window doubles as a "touched" flag (1.0) until C overwrites it
-                //    with the dot products: a pixel touched with zero total weight still needs its d.
-                for (int s = lane; s < ny * kWinSide; s += G) { win[s] = 0.f; dot[s] = 0.f; }
+            if (nx > 0 && ny > 0 && nx <= kWinSide && ny <= kWinSide && S <= 3.0e38f) {
+                // B: pixel weights (fixed point).  The d window doubles as a "touched" flag (1.0) until C
+                //    overwrites it with the dot products: a pixel touched with zero total weight still needs its d.
+                const int ke = fixed_scale_exp(fmaxf(S, 1e-30f));
+                const float scale = pow2f(ke), inv_scale = pow2f(-ke);
+                for (int s = lane; s < ny * kWinSide; s += G) { win[s] = 0; dot[s] = 0.f; }
                 __syncwarp(gm);
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     if (pt[k].inside) {
                         const int sx = pt[k].x0 - X0, sy = pt[k].y0 - Y0;
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
+                        const float a = pt[k].aw * scale;
                         const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
                         const int s00 = sy * kWinSide + sx;
-                        if (vy0 && vx0) { atomicAdd(win + s00, hy * hx * pt[k].aw); dot[s00] = 1.f; }
-                        if (vy0 && vx1) { atomicAdd(win + s00 + 1, hy * pt[k].lx * pt[k].aw); dot[s00 + 1] = 1.f; }
-                        if (vy1 && vx0) { atomicAdd(win + s00 + kWinSide, pt[k].ly * hx * pt[k].aw); dot[s00 + kWinSide] = 1.f; }
-                        if (vy1 && vx1) { atomicAdd(win + s00 + kWinSide + 1, pt[k].ly * pt[k].lx * pt[k].aw); dot[s00 + kWinSide + 1] = 1.f; }
+                        if (vy0 && vx0) { atomicAdd(win + s00, __float2int_rn(hy * hx * a)); dot[s00] = 1.f; }
+                        if (vy0 && vx1) { atomicAdd(win + s00 + 1, __float2int_rn(hy * pt[k].lx * a)); dot[s00 + 1] = 1.f; }
+                        if (vy1 && vx0) { atomicAdd(win + s00 + kWinSide, __float2int_rn(pt[k].ly * hx * a)); dot[s00 + kWinSide] = 1.f; }
+                        if (vy1 && vx1) { atomicAdd(win + s00 + kWinSide + 1, __float2int_rn(pt[k].ly * pt[k].lx * a)); dot[s00 + kWinSide + 1] = 1.f; }
                     }
                 }
                 __syncwarp(gm);
-                // C: per unique pixel: value row, scatter W*go, d = <go, v>
+                // C: per unique pixel, four pixels (half a window row) at a time:
+                //    value row -> scatter W*go into grad_value, d = <go, v> by transpose reduction
                 const long long wbase = lbase + ((long long)Y0 * lw + X0) * HD;
+                const int nhalf = nx > 4 ? 2 : 1;
                 for (int iy = 0; iy < ny; ++iy) {
-                    const float4 wa = *reinterpret_cast<const float4*>(win + iy * kWinSide);
-                    const float4 wb = *reinterpret_cast<const float4*>(win + iy * kWinSide + 4);
-                    const float4 ta = *reinterpret_cast<const float4*>(dot + iy * kWinSide);
-                    const float4 tb = *reinterpret_cast<const float4*>(dot + iy * kWinSide + 4);
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                    const float tv[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-                    const long long rbase = wbase + (long long)iy * lw * HD;
-                    float v[8][VEC];
+                    for (int hf = 0; hf < nhalf; ++hf) {
+                        const int sbase = iy * kWinSide + hf * 4;
+                        const int4 wq = *reinterpret_cast<const int4*>(win + sbase);
+                        const float4 tq = *reinterpret_cast<const float4*>(dot + sbase);
+                        const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
+                        const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                        const long long rbase = wbase + ((long long)iy * lw + hf * 4) * HD;
+                        float v[4][VEC];
 #pragma unroll
-                    for (int ix = 0; ix < 8; ++ix) {
-                        if (ix < nx && tv[ix] != 0.f) {
-                            V::load(value + rbase + ix * HD, v[ix]);
-                        } else {
+                        for (int ix = 0; ix < 4; ++ix) {
+                            if (hf * 4 + ix < nx && tv[ix] != 0.f) {
+                                V::load(value + rbase + ix * HD, v[ix]);
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < VEC; ++i) v[ix][i] = 0.f;
+                                for (int i = 0; i < VEC; ++i) v[ix][i] = 0.f;
+                            }
                         }
-                    }
-                    __syncwarp(gm);      // all lanes have read the touched flags of this window row
-                    float dsum[8];
+                        float dsum[4];
 #pragma unroll
-                    for (int ix = 0; ix < 8; ++ix) {
-                        float s = 0.f;
+                        for (int ix = 0; ix < 4; ++ix) {
+                            float s = 0.f;
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) s += go[i] * v[ix][i];
-                        dsum[ix] = s;
-                        if (ix < nx && wv[ix] != 0.f) scatter_row<ACC, VEC>(gacc + rbase + ix * HD, go, wv[ix], dscale);
-                    }
-                    // transpose-reduce the 8 partial dot products over the G lanes
-#pragma unroll
-                    for (int ix = 0; ix < 8; ++ix) dsum[ix] = gsum<G>(dsum[ix], gm);
-                    if (lane == 0) {
-                        *reinterpret_cast<float4*>(dot + iy * kWinSide) = make_float4(dsum[0], dsum[1], dsum[2], dsum[3]);
-                        *reinterpret_cast<float4*>(dot + iy * kWinSide + 4) = make_float4(dsum[4], dsum[5], dsum[6], dsum[7]);
+                            for (int i = 0; i < VEC; ++i) s += go[i] * v[ix][i];
+                            dsum[ix] = s;
+                            if (hf * 4 + ix < nx && wi[ix] != 0)
+                                scatter_row<ACC, VEC>(gacc + rbase + ix * HD, go, (float)wi[ix] * inv_scale, dscale);
+                        }
+                        float total;
+                        const int mine = reduce4<G>(dsum, total, lane, gm);   // also orders the flag reads before the writes
+                        dot[sbase + mine] = total;                             // lanes sharing an index write the same value
                     }
                 }
                 __syncwarp(gm);
@@ -365,7 +421,7 @@ __global__ void __launch_bounds__(kThreads) box_bwd_win_kernel(const AttnParams 
                 }
                 __syncwarp(gm);
             } else if (nx > 0 && ny > 0) {
-                // per-point fallback (window too large)
+                // per-point fallback (window too large, or non-finite weights)
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     for (int o = 0; o < G; ++o) {

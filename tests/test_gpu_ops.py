@@ -72,6 +72,31 @@ def _run_inst(inp, dtype, grad_out=None, grad_mask=None, deterministic=False):
     return out.detach(), mask.detach(), (value.grad, loc.grad, sw.grad, lw.grad)
 
 
+def _near_cell_boundary(loc, shapes, eps=2e-3):
+    """(B,Nq,H,L,P) mask of sample points within `eps` pixels of a pixel-grid line.  The bilinear
+    interpolant is continuous there but its derivative w.r.t. the location is not: an fp32 kernel
+    and an fp64 oracle can legitimately pick different cells (the fp32 rounding of loc*size-0.5 is
+    ~1.5e-5 px at x~167), which changes grad_loc of that one point by O(1).  Such points are left out
+    of the grad_loc comparison only; every other output is continuous and is compared everywhere."""
+    loc = loc.detach().double().cpu()
+    sh = torch.as_tensor(shapes).cpu()
+    near = torch.zeros(loc.shape[:-1], dtype=torch.bool)
+    for l in range(sh.shape[0]):
+        for c, size in ((0, float(sh[l, 1])), (1, float(sh[l, 0]))):
+            x = loc[:, :, :, l, :, c] * size - 0.5
+            f = x - torch.floor(x)
+            near[:, :, :, l] |= (f < eps) | (f > 1 - eps)
+    return near
+
+
+def _close_grad_loc(got, want, loc, shapes, tol, what="grad_loc"):
+    keep = (~_near_cell_boundary(loc, shapes))[..., None]
+    got = torch.as_tensor(got).detach().double().cpu().view(*keep.shape[:-1], 2) * keep
+    want = torch.as_tensor(want).double().cpu().view(*keep.shape[:-1], 2) * keep
+    assert float(keep.double().mean()) > 0.9
+    _close(got, want, tol, what)
+
+
 def _close(got, want, tol, what):
     want = torch.as_tensor(want)
     err = helpers.rel_err(got, want)
@@ -212,8 +237,13 @@ def test_box_c1_scale_vs_oracle(K, oob, dtype):
     ref_out, ref_grads = _oracle_box(w, go)
     tol = TOL[dtype]
     _close(out, ref_out, tol, "out")
-    for g, r, k in zip(grads, ref_grads, ("grad_value", "grad_loc", "grad_attn")):
-        _close(g, r.view_as(g), tol, k)
+    _compare_box_grads(grads, ref_grads, w, tol)
+
+
+def _compare_box_grads(grads, ref_grads, w, tol, tag=""):
+    _close(grads[0], ref_grads[0].view_as(grads[0]), tol, "grad_value" + tag)
+    _close_grad_loc(grads[1], ref_grads[1], w.loc, w.shapes, tol, "grad_loc" + tag)
+    _close(grads[2], ref_grads[2].view_as(grads[2]), tol, "grad_attn" + tag)
 
 
 @pytest.mark.parametrize("maker,kw", [
@@ -230,8 +260,7 @@ def test_box_decoder_like_vs_oracle(maker, kw):
     out, grads = _run_box(_wl_inputs(w), torch.float32, go)
     ref_out, ref_grads = _oracle_box(w, go)
     _close(out, ref_out, 1e-4, "out")
-    for g, r, k in zip(grads, ref_grads, ("grad_value", "grad_loc", "grad_attn")):
-        _close(g, r.view_as(g), 1e-4, k)
+    _compare_box_grads(grads, ref_grads, w, 1e-4)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
@@ -257,7 +286,10 @@ def test_instance_mask_head_vs_oracle(K, Nq, dtype):
     _close(out, ro, tol, "out")
     _close(mask, rm.view_as(mask), tol, "mask_out")
     for g, r, k in zip(grads, rg, ("grad_value", "grad_loc", "grad_spatial_w", "grad_level_w")):
-        _close(g, r.view_as(g), tol, k)
+        if k == "grad_loc":
+            _close_grad_loc(g, r, w.loc, w.shapes, tol)
+        else:
+            _close(g, r.view_as(g), tol, k)
 
 
 # ============================================================== footprint-window kernels, forced at small sizes
@@ -294,10 +326,8 @@ def test_window_kernels_vs_oracle(case, dtype):
     ref_out, ref_grads = _oracle_box(w, go)
     tol = TOL[dtype]
     _close(out, ref_out, tol, "out")
-    for g, r, k in zip(grads, ref_grads, ("grad_value", "grad_loc", "grad_attn")):
-        _close(g, r.view_as(g), tol, k)
-    for g, r, k in zip(det, ref_grads, ("grad_value", "grad_loc", "grad_attn")):
-        _close(g, r.view_as(g), tol, k + " (deterministic)")
+    _compare_box_grads(grads, ref_grads, w, tol)
+    _compare_box_grads(det, ref_grads, w, tol, " (deterministic)")
     # and the point kernels agree with the window kernels
     b.ops.set_kernel_path("point")
     try:
@@ -331,7 +361,7 @@ def test_coco_encoder_full_size(dist):
     ref_out = kernel_ref.box_attn_forward(*sl)
     _, ref_gl, ref_ga = kernel_ref.box_attn_backward(*sl, cpu(go[:, idx]))
     _close(out[:, idx], ref_out, 1e-4, "out[slice]")
-    _close(loc.grad[:, idx], ref_gl, 1e-4, "grad_loc[slice]")
+    _close_grad_loc(loc.grad[:, idx], ref_gl, w.loc[:, idx], w.shapes, 1e-4, "grad_loc[slice]")
     _close(attn.grad[:, idx], ref_ga.view_as(attn.grad[:, idx]), 1e-4, "grad_attn[slice]")
 
     lhs = (out.detach().double() * go.double()).sum()
