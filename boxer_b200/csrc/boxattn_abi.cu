@@ -161,6 +161,8 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
     if (flags & BXR_FLAG_PATH_POINT) return false;
     if (g != 4 && g != 8 && g != 16) return false;
     if (p.P > 4 * g || p.P < 1) return false;
+    // the window kernels address value in 16-byte units with 32-bit indices
+    if ((long long)p.B * p.S * g * p.H >= 0xffffffffLL) return false;
     if (flags & BXR_FLAG_PATH_WINDOW) return true;
     if (p.P < 8) return false;                      // 2x2 grids: too few points per level to amortise the window
     const long long groups = kThreads / g;

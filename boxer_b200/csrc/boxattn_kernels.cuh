@@ -84,6 +84,11 @@ template <> struct Vec16<float> {
     __device__ __forceinline__ static void store(float* p, const float (&v)[4]) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    // 16-byte-unit index off a uniform base: one IMAD.WIDE.U32 of address math per load
+    __device__ __forceinline__ static void load16(const uint4* base, unsigned idx, float (&v)[4]) {
+        const uint4 t = __ldg(base + idx);
+        v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+    }
 };
 template <> struct Vec16<__nv_bfloat16> {
     static constexpr int VEC = 8;
@@ -92,6 +97,15 @@ template <> struct Vec16<__nv_bfloat16> {
         const unsigned u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {   // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(u[i] << 16);
+            v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+        }
+    }
+    __device__ __forceinline__ static void load16(const uint4* base, unsigned idx, float (&v)[8]) {
+        const uint4 t = __ldg(base + idx);
+        const unsigned u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
             v[2 * i] = __uint_as_float(u[i] << 16);
             v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
         }

@@ -10,7 +10,7 @@
 // So, per (row = (b, q, head), level):
 //   A. the G lanes of the row's group each take P/G points (coalesced loc / weight loads),
 //      compute their taps once, and min/max-reduce the touched pixel range with shuffles;
-//   B. if the range fits an 8 x 8 window, the lanes scatter  attn * bilinear weight  of their
+//   B. if the range fits a 64-pixel window, the lanes scatter  attn * bilinear weight  of their
 //      points' corners into a per-group window of pixel weights in shared memory;
 //   C. the group walks the window: one 16-byte row load per *unique* pixel,
 //         forward :  acc        += W[pix] * value[pix]
@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
     const int gid = threadIdx.x / G;
     const unsigned gm = group_mask<G>();
     int* win = s_win + gid * kWinPitch;
-    const int HD = p.H * p.D;
-    const TV* __restrict__ value = static_cast<const TV*>(p.value);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in 16-byte units
+    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
 
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
         if (row >= p.rows) continue;            // whole group leaves; everything below is group-scoped
         const int head = (int)(row % p.H);
         const long long b = row / ((long long)p.H * p.Nq);
-        const TV* vrow = value + (b * p.S * HD + head * p.D + lane * VEC);
+        // value addressing in 16-byte units (one lane chunk) as 32-bit indices off the tensor base
+        const unsigned vrow = (unsigned)(b * p.S * HDV + head * G + lane);
         const float* loc_row = loc + row * p.LP * 2;
         const float* w_row = w0 + row * p.LP;
 
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
 
         for (int l = 0; l < p.L; ++l) {
             const int lh = lv.h[l], lw = lv.w[l];
-            const TV* vlev = vrow + lv.start[l] * HD;
+            const unsigned vlev = vrow + (unsigned)lv.start[l] * HDV;
             // ---- A: own points, touched pixel range
             LanePoint pt[PPL];
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
@@ -156,11 +157,12 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
             if (S == 0.f) continue;             // every weight of this level is exactly zero
 
             // non-finite weights (S is NaN/inf) take the float path below so that they propagate
-            if (nx <= kWinSide && ny <= kWinSide && S <= 3.0e38f) {
-                // ---- B: scatter pixel weights into the window (32-bit fixed point, see fixed_scale_exp)
+            const int nq = nx * ny;
+            if (nq <= kWinSlots && S <= 3.0e38f) {
+                // ---- B: scatter pixel weights into the dense nx x ny window (32-bit fixed point)
                 const int ke = fixed_scale_exp(S);
                 const float scale = pow2f(ke), inv_scale = pow2f(-ke);
-                for (int s = lane; s < ny * kWinSide; s += G) win[s] = 0;
+                for (int s = lane; s < ((nq + 3) & ~3); s += G) win[s] = 0;
                 __syncwarp(gm);
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
@@ -169,38 +171,42 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
                         const float a = pt[k].aw * scale;
                         const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
-                        int* wp = win + sy * kWinSide + sx;
+                        int* wp = win + sy * nx + sx;
                         if (vy0 && vx0) atomicAdd(wp, __float2int_rn(hy * hx * a));
                         if (vy0 && vx1) atomicAdd(wp + 1, __float2int_rn(hy * pt[k].lx * a));
-                        if (vy1 && vx0) atomicAdd(wp + kWinSide, __float2int_rn(pt[k].ly * hx * a));
-                        if (vy1 && vx1) atomicAdd(wp + kWinSide + 1, __float2int_rn(pt[k].ly * pt[k].lx * a));
+                        if (vy1 && vx0) atomicAdd(wp + nx, __float2int_rn(pt[k].ly * hx * a));
+                        if (vy1 && vx1) atomicAdd(wp + nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a));
                     }
                 }
                 __syncwarp(gm);
-                // ---- C: one row load per unique pixel
-                const TV* wbase = vlev + ((long long)Y0 * lw + X0) * HD;
-                for (int iy = 0; iy < ny; ++iy) {
-                    const int4 wa = *reinterpret_cast<const int4*>(win + iy * kWinSide);
-                    const int4 wb = *reinterpret_cast<const int4*>(win + iy * kWinSide + 4);
-                    const int wi[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                    float wv[8];
+                // ---- C: one row load per unique pixel, four window slots at a time; the pixel offset is
+                //         advanced incrementally (no division by nx)
+                const unsigned row_skip = (unsigned)(lw - nx) * HDV;
+                unsigned off = vlev + (unsigned)(Y0 * lw + X0) * HDV;
+                int ix = 0;
+#pragma unroll 2
+                for (int q = 0; q < nq; q += 4) {
+                    const int4 wq = *reinterpret_cast<const int4*>(win + q);
+                    const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
+                    unsigned offs[4];
 #pragma unroll
-                    for (int ix = 0; ix < 8; ++ix) wv[ix] = (float)wi[ix] * inv_scale;
-                    const TV* rbase = wbase + (long long)iy * lw * HD;
-                    float v[8][VEC];
+                    for (int j = 0; j < 4; ++j) {
+                        offs[j] = off;
+                        off += HDV;
+                        if (++ix == nx) { ix = 0; off += row_skip; }
+                    }
+                    float v[4][VEC];
 #pragma unroll
-                    for (int ix = 0; ix < 8; ++ix) {
-                        if (ix < nx && wi[ix] != 0) {
-                            V::load(rbase + ix * HD, v[ix]);
-                        } else {
+                    for (int j = 0; j < 4; ++j)
+                        if (wi[j] != 0) V::load16(value16, offs[j], v[j]);   // slots past nq were zeroed and never written
 #pragma unroll
-                            for (int i = 0; i < VEC; ++i) v[ix][i] = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        if (wi[j] != 0) {
+                            const float wv = (float)wi[j] * inv_scale;
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc[i] += wv * v[j][i];
                         }
                     }
-#pragma unroll
-                    for (int ix = 0; ix < 8; ++ix)
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) acc[i] += wv[ix] * v[ix][i];
                 }
                 __syncwarp(gm);   // the window is re-zeroed by the next level
             } else {
@@ -218,12 +224,12 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
                         const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= lw - 1, vy0 = y0 >= 0, vy1 = y0 + 1 <= lh - 1;
                         const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
                         const float cw[4] = {hy * hx * aw, hy * lx * aw, ly * hx * aw, ly * lx * aw};
-                        const TV* c00 = vlev + ((long long)y0 * lw + x0) * HD;
+                        const unsigned c00 = vlev + (unsigned)(y0 * lw + x0) * HDV;   // wraps for x0/y0 = -1; valid corners are right
                         float v[4][VEC];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (ok[c]) {
-                                V::load(c00 + ((c & 1) ? HD : 0) + ((c & 2) ? (long long)lw * HD : 0), v[c]);
+                                V::load16(value16, c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u), v[c]);
                             } else {
 #pragma unroll
                                 for (int i = 0; i < VEC; ++i) v[c][i] = 0.f;
@@ -297,8 +303,8 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
     const unsigned gm = group_mask<G>();
     int* win = s_win + gid * kWinPitch;
     float* dot = s_dot + gid * kWinPitch;
-    const int HD = p.H * p.D;
-    const TV* __restrict__ value = static_cast<const TV*>(p.value);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in 16-byte units
+    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
     ACC* __restrict__ gacc = static_cast<ACC*>(p.grad_value_acc);
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
         if (row >= p.rows) continue;
         const int head = (int)(row % p.H);
         const long long b = row / ((long long)p.H * p.Nq);
-        const long long vbase = b * p.S * HD + head * p.D + lane * VEC;
+        const unsigned vbase = (unsigned)(b * p.S * HDV + head * G + lane);
         const float* loc_row = loc + row * p.LP * 2;
         const float* w_row = w0 + row * p.LP;
         float go[VEC];
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
 
         for (int l = 0; l < p.L; ++l) {
             const int lh = lv.h[l], lw = lv.w[l];
-            const long long lbase = vbase + lv.start[l] * HD;
+            const unsigned lbase = vbase + (unsigned)lv.start[l] * HDV;
             LanePoint pt[PPL];
             float g_a[PPL], g_x[PPL], g_y[PPL];     // this lane's results for its own points
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
@@ -342,12 +348,14 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
             const int nx = X1 - X0 + 1, ny = Y1 - Y0 + 1;
             S = gsum<G>(S, gm);
 
-            if (nx > 0 && ny > 0 && nx <= kWinSide && ny <= kWinSide && S <= 3.0e38f) {
-                // B: pixel weights (fixed point).  The d window doubles as a "touched" flag (1.0) until C
-                //    overwrites it with the dot products: a pixel touched with zero total weight still needs its d.
+            const int nq = nx * ny;
+            if (nx > 0 && ny > 0 && nq <= kWinSlots && S <= 3.0e38f) {
+                // B: pixel weights (fixed point) in a dense nx x ny window.  The d window doubles as a
+                //    "touched" flag (1.0) until C overwrites it with the dot products: a pixel touched
+                //    with zero total weight still needs its d.
                 const int ke = fixed_scale_exp(fmaxf(S, 1e-30f));
                 const float scale = pow2f(ke), inv_scale = pow2f(-ke);
-                for (int s = lane; s < ny * kWinSide; s += G) { win[s] = 0; dot[s] = 0.f; }
+                for (int s = lane; s < ((nq + 3) & ~3); s += G) { win[s] = 0; dot[s] = 0.f; }
                 __syncwarp(gm);
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
@@ -356,50 +364,53 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
                         const float a = pt[k].aw * scale;
                         const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
-                        const int s00 = sy * kWinSide + sx;
+                        const int s00 = sy * nx + sx;
                         if (vy0 && vx0) { atomicAdd(win + s00, __float2int_rn(hy * hx * a)); dot[s00] = 1.f; }
                         if (vy0 && vx1) { atomicAdd(win + s00 + 1, __float2int_rn(hy * pt[k].lx * a)); dot[s00 + 1] = 1.f; }
-                        if (vy1 && vx0) { atomicAdd(win + s00 + kWinSide, __float2int_rn(pt[k].ly * hx * a)); dot[s00 + kWinSide] = 1.f; }
-                        if (vy1 && vx1) { atomicAdd(win + s00 + kWinSide + 1, __float2int_rn(pt[k].ly * pt[k].lx * a)); dot[s00 + kWinSide + 1] = 1.f; }
+                        if (vy1 && vx0) { atomicAdd(win + s00 + nx, __float2int_rn(pt[k].ly * hx * a)); dot[s00 + nx] = 1.f; }
+                        if (vy1 && vx1) { atomicAdd(win + s00 + nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a)); dot[s00 + nx + 1] = 1.f; }
                     }
                 }
                 __syncwarp(gm);
-                // C: per unique pixel, four pixels (half a window row) at a time:
+                // C: per unique pixel, four window slots at a time:
                 //    value row -> scatter W*go into grad_value, d = <go, v> by transpose reduction
-                const long long wbase = lbase + ((long long)Y0 * lw + X0) * HD;
-                const int nhalf = nx > 4 ? 2 : 1;
-                for (int iy = 0; iy < ny; ++iy) {
-                    for (int hf = 0; hf < nhalf; ++hf) {
-                        const int sbase = iy * kWinSide + hf * 4;
-                        const int4 wq = *reinterpret_cast<const int4*>(win + sbase);
-                        const float4 tq = *reinterpret_cast<const float4*>(dot + sbase);
-                        const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
-                        const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
-                        const long long rbase = wbase + ((long long)iy * lw + hf * 4) * HD;
-                        float v[4][VEC];
+                const unsigned row_skip = (unsigned)(lw - nx) * HDV;
+                unsigned off = lbase + (unsigned)(Y0 * lw + X0) * HDV;
+                int ix = 0;
+                for (int q = 0; q < nq; q += 4) {
+                    const int4 wq = *reinterpret_cast<const int4*>(win + q);
+                    const float4 tq = *reinterpret_cast<const float4*>(dot + q);
+                    const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
+                    const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                    unsigned offs[4];
 #pragma unroll
-                        for (int ix = 0; ix < 4; ++ix) {
-                            if (hf * 4 + ix < nx && tv[ix] != 0.f) {
-                                V::load(value + rbase + ix * HD, v[ix]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < VEC; ++i) v[ix][i] = 0.f;
-                            }
-                        }
-                        float dsum[4];
-#pragma unroll
-                        for (int ix = 0; ix < 4; ++ix) {
-                            float s = 0.f;
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) s += go[i] * v[ix][i];
-                            dsum[ix] = s;
-                            if (hf * 4 + ix < nx && wi[ix] != 0)
-                                scatter_row<ACC, VEC>(gacc + rbase + ix * HD, go, (float)wi[ix] * inv_scale, dscale);
-                        }
-                        float total;
-                        const int mine = reduce4<G>(dsum, total, lane, gm);   // also orders the flag reads before the writes
-                        dot[sbase + mine] = total;                             // lanes sharing an index write the same value
+                    for (int j = 0; j < 4; ++j) {
+                        offs[j] = off;
+                        off += HDV;
+                        if (++ix == nx) { ix = 0; off += row_skip; }
                     }
+                    float v[4][VEC];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (tv[j] != 0.f) {        // slots past nq were zeroed and never flagged
+                            V::load16(value16, offs[j], v[j]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
+                        }
+                    }
+                    float dsum[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = 0.f;
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
+                        dsum[j] = t;
+                        if (wi[j] != 0) scatter_row<ACC, VEC>(gacc + (size_t)offs[j] * VEC, go, (float)wi[j] * inv_scale, dscale);
+                    }
+                    float total;
+                    const int mine = reduce4<G>(dsum, total, lane, gm);   // also orders the flag reads before the writes
+                    dot[q + mine] = total;                                 // lanes sharing an index write the same value
                 }
                 __syncwarp(gm);
                 // D: finish own points from the d window
@@ -409,11 +420,11 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
                         const int sx = pt[k].x0 - X0, sy = pt[k].y0 - Y0;
                         const float lx = pt[k].lx, ly = pt[k].ly, hx = 1.f - lx, hy = 1.f - ly;
                         const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
-                        const int s00 = sy * kWinSide + sx;
+                        const int s00 = sy * nx + sx;
                         const float d00 = (vy0 && vx0) ? dot[s00] : 0.f;
                         const float d01 = (vy0 && vx1) ? dot[s00 + 1] : 0.f;
-                        const float d10 = (vy1 && vx0) ? dot[s00 + kWinSide] : 0.f;
-                        const float d11 = (vy1 && vx1) ? dot[s00 + kWinSide + 1] : 0.f;
+                        const float d10 = (vy1 && vx0) ? dot[s00 + nx] : 0.f;
+                        const float d11 = (vy1 && vx1) ? dot[s00 + nx + 1] : 0.f;
                         g_a[k] = hy * hx * d00 + hy * lx * d01 + ly * hx * d10 + ly * lx * d11;
                         g_x[k] = (float)lw * pt[k].aw * (hy * (d01 - d00) + ly * (d11 - d10));
                         g_y[k] = (float)lh * pt[k].aw * (hx * (d10 - d00) + lx * (d11 - d01));
@@ -435,18 +446,18 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
                         const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= lw - 1, vy0 = y0 >= 0, vy1 = y0 + 1 <= lh - 1;
                         const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
                         const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
-                        const long long c00 = lbase + ((long long)y0 * lw + x0) * HD;
+                        const unsigned c00 = lbase + (unsigned)(y0 * lw + x0) * HDV;
                         float d[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             float s = 0.f;
                             if (ok[c]) {
-                                const long long off = c00 + ((c & 1) ? HD : 0) + ((c & 2) ? (long long)lw * HD : 0);
+                                const unsigned off = c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u);
                                 float v[VEC];
-                                V::load(value + off, v);
+                                V::load16(value16, off, v);
 #pragma unroll
                                 for (int i = 0; i < VEC; ++i) s += go[i] * v[i];
-                                scatter_row<ACC, VEC>(gacc + off, go, cw[c] * aw, dscale);
+                                scatter_row<ACC, VEC>(gacc + (size_t)off * VEC, go, cw[c] * aw, dscale);
                             }
                             d[c] = s;
                         }

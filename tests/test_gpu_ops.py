@@ -37,9 +37,10 @@ def _run_box(inp, dtype, grad_out=None, deterministic=False):
     b = _ops()
     tw = torch.float64 if dtype == torch.float64 else torch.float32
     g = _cuda(inp)
-    value = g["value"].to(dtype).requires_grad_(grad_out is not None)
-    loc = g["loc"].to(tw).requires_grad_(grad_out is not None)
-    attn = g["attn"].to(tw).requires_grad_(grad_out is not None)
+    # fresh leaves every call (.to() is a no-op for a matching dtype and .grad would accumulate)
+    value = g["value"].detach().to(dtype).clone().requires_grad_(grad_out is not None)
+    loc = g["loc"].detach().to(tw).clone().requires_grad_(grad_out is not None)
+    attn = g["attn"].detach().to(tw).clone().requires_grad_(grad_out is not None)
     b.set_deterministic(deterministic)
     try:
         out = b.BoxAttnFunction.apply(value, g["shapes"], g["level_start"], loc, attn, 64)
@@ -56,10 +57,10 @@ def _run_inst(inp, dtype, grad_out=None, grad_mask=None, deterministic=False):
     tw = torch.float64 if dtype == torch.float64 else torch.float32
     need = grad_out is not None
     g = _cuda(inp)
-    value = g["value"].to(dtype).requires_grad_(need)
-    loc = g["loc"].to(tw).requires_grad_(need)
-    sw = g["spatial_w"].to(tw).requires_grad_(need)
-    lw = g["level_w"].to(tw).requires_grad_(need)
+    value = g["value"].detach().to(dtype).clone().requires_grad_(need)
+    loc = g["loc"].detach().to(tw).clone().requires_grad_(need)
+    sw = g["spatial_w"].detach().to(tw).clone().requires_grad_(need)
+    lw = g["level_w"].detach().to(tw).clone().requires_grad_(need)
     b.set_deterministic(deterministic)
     try:
         out, mask = b.InstanceAttnFunction.apply(value, g["shapes"], g["level_start"], loc, sw, lw, inp["mask_size"], 64)
