@@ -120,6 +120,19 @@ def step_resident(ops, w, go):
     return out, grads, n + ops.last_launch_count()
 
 
+def max_over_ranks(ms: float, device) -> float:
+    """A multi-GPU number is the slowest rank's device time (never wall clock, never the mean)."""
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def rank_seed(rank: int, base: int = 3) -> int:
+    """Images shard over ranks (no collective in the op): every rank draws its own images."""
+    return base + 10 * rank
+
+
 def timed(fn, steps, warmup, dist_on):
     """W warm-up steps, then exactly K steps between barrier+synchronize pairs, CUDA events; max over ranks."""
     import torch.distributed as dist
@@ -140,9 +153,7 @@ def timed(fn, steps, warmup, dist_on):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if dist_on:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = max_over_ranks(ms, "cuda")
     return ms
 
 
@@ -356,7 +367,7 @@ def main():
     from boxer_b200 import workloads as W
 
     bw_peak, peak_src = peaks()
-    sets = make_sets(dev, 2, seed0=3 + 10 * rank, K=CFG["K"], dist=CFG["dist"], B=CFG["B_per_gpu"])
+    sets = make_sets(dev, 2, seed0=rank_seed(rank), K=CFG["K"], dist=CFG["dist"], B=CFG["B_per_gpu"])
     n_samples = sets[0][0].n_samples
     launches = [0]
 
@@ -393,10 +404,10 @@ def main():
         "config": dict(CFG, n_samples_per_gpu_step=n_samples,
                        l2="working set ~364 MB/step (> 126 MB L2); 2 rotating input sets; no explicit flush",
                        locations="box-structured (encoder reference windows + init-state offsets), see boxer_b200/workloads.py"),
-        "roofline": {"bound": "hbm", "kernel": "attn_bwd_vec_kernel<float,8,box,atomic> (+ grad_value memset)",
+        "roofline": {"bound": "hbm", "kernel": "box_bwd_win_kernel<float,8,2,atomic> (+ grad_value memset)",
                      "achieved": ach_b, "peak": bw_peak, "unit": "GB/s", "frac": ach_b / bw_peak, "traffic": None,
                      "peak_source": peak_src, "bytes_per_sample": bb, "ms_per_launch": kb_ms},
-        "roofline_fwd": {"bound": "hbm", "kernel": "attn_fwd_vec_kernel<float,8,box,U=4>", "achieved": ach_f, "peak": bw_peak,
+        "roofline_fwd": {"bound": "hbm", "kernel": "box_fwd_win_kernel<float,8,2>", "achieved": ach_f, "peak": bw_peak,
                          "unit": "GB/s", "frac": ach_f / bw_peak, "traffic": None, "bytes_per_sample": bf,
                          "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6},
         "roofline_step": {"achieved": ach_s, "frac": ach_s / bw_peak, "unit": "GB/s"},

@@ -117,9 +117,9 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
 
-    int u0, u1;
-    unit_range(p.units, u0, u1);
-    for (int u = u0; u < u1; ++u) {
+    // units are dealt round-robin: rows of the coarse levels (wide windows -> per-point fallback) cost
+    // several times more than level-0 rows, and a contiguous split leaves the CTAs that own them as a tail
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const long long row = (long long)u * GROUPS + gid;
         if (row >= p.rows) continue;            // whole group leaves; everything below is group-scoped
         const int head = (int)(row % p.H);
@@ -313,9 +313,9 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
     float dscale = 1.f;
     if constexpr (DET) dscale = *p.det_scale;
 
-    int u0, u1;
-    unit_range(p.units, u0, u1);
-    for (int u = u0; u < u1; ++u) {
+    // units are dealt round-robin: rows of the coarse levels (wide windows -> per-point fallback) cost
+    // several times more than level-0 rows, and a contiguous split leaves the CTAs that own them as a tail
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const long long row = (long long)u * GROUPS + gid;
         if (row >= p.rows) continue;
         const int head = (int)(row % p.H);

@@ -13,6 +13,7 @@ tail -5 $OUT/pytest.log
 timeout 600 python bench.py --variants > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 cat $OUT/bench.json; tail -30 $OUT/bench.err
 cp gpurun_out/variants.json $OUT/variants.json 2>/dev/null
+timeout 300 python scripts/compare_reference_cuda.py $OUT/vs_reference_cuda.json > $OUT/vs_reference_cuda.log 2>&1; tail -8 $OUT/vs_reference_cuda.log
 if [ "$MODE" != "quick" ]; then
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:attn_|box_|absmax|finalize|det_scale" -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
