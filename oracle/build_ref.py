@@ -43,8 +43,8 @@ def main():
         name=NAME,
         sources=sources,
         extra_include_paths=[SRC],
-        extra_cflags=["-O2", "-include", shim],
-        extra_cuda_cflags=["-O3", "-DCUDA_HAS_FP16=1", "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__",
+        extra_cflags=["-O2", "-DWITH_CUDA", "-include", shim],   # WITH_CUDA: setup.py:47
+        extra_cuda_cflags=["-O3", "-DWITH_CUDA", "-DCUDA_HAS_FP16=1", "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__",
                            "-D__CUDA_NO_HALF2_OPERATORS__", "-include", shim,
                            "-gencode", "arch=compute_100a,code=sm_100a"],
         build_directory=os.path.join(OUT, "build"),
