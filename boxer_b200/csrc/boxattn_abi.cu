@@ -164,47 +164,51 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
     // the window kernels address value in 16-byte units with 32-bit indices
     if ((long long)p.B * p.S * g * p.H >= 0xffffffffLL) return false;
     if (flags & BXR_FLAG_PATH_WINDOW) return true;
-    if (p.P < 8) return false;                      // 2x2 grids: too few points per level to amortise the window
+    if (p.P < 3) return false;
     const long long groups = kThreads / g;
     return p.rows >= 2LL * sm_count() * groups;     // small (decoder-sized) calls keep the point-split kernels
 }
 
-template <typename TV, int G, int PPL>
+template <typename TV, int G, int SUB, int PPL>
 int fwd_win(AttnParams& p, cudaStream_t st) {
     p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_fwd_win_kernel<TV, G, PPL>>(p, st, "box_fwd_win_kernel");
+    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL>>(p, st, "box_fwd_win_kernel");
 }
-template <typename TV, int G, int PPL, typename ACC>
+template <typename TV, int G, int SUB, int PPL, typename ACC>
 int bwd_win(AttnParams& p, cudaStream_t st) {
     p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_bwd_win_kernel<TV, G, PPL, ACC>>(p, st, "box_bwd_win_kernel");
+    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC>>(p, st, "box_bwd_win_kernel");
 }
 
-#define BXR_DISPATCH_WIN(G_, PPL_, CALL)                                                      \
-    switch ((G_) * 8 + (PPL_)) {                                                              \
-        case 4 * 8 + 1: { constexpr int G = 4, PPL = 1; return CALL; }                        \
-        case 4 * 8 + 2: { constexpr int G = 4, PPL = 2; return CALL; }                        \
-        case 4 * 8 + 4: { constexpr int G = 4, PPL = 4; return CALL; }                        \
-        case 8 * 8 + 1: { constexpr int G = 8, PPL = 1; return CALL; }                        \
-        case 8 * 8 + 2: { constexpr int G = 8, PPL = 2; return CALL; }                        \
-        case 8 * 8 + 4: { constexpr int G = 8, PPL = 4; return CALL; }                        \
-        case 16 * 8 + 1: { constexpr int G = 16, PPL = 1; return CALL; }                      \
-        case 16 * 8 + 2: { constexpr int G = 16, PPL = 2; return CALL; }                      \
-        default: { constexpr int G = 16, PPL = 4; return CALL; }                              \
+// (G, SUB, PPL): SUB lanes share a level's points, PPL points per lane; P <= SUB * PPL.
+// P <= G/2 packs two levels per pass (SUB = G/2) so that 2x2 grids keep all lanes busy.
+#define BXR_WIN_CASE(G_, SUB_, PPL_, CALL) \
+    case (G_) * 1000 + (SUB_) * 10 + (PPL_): { constexpr int G = G_, SUB = SUB_, PPL = PPL_; return CALL; }
+#define BXR_DISPATCH_WIN(KEY, CALL)                                                        \
+    switch (KEY) {                                                                         \
+        BXR_WIN_CASE(4, 4, 1, CALL) BXR_WIN_CASE(4, 4, 2, CALL) BXR_WIN_CASE(4, 4, 4, CALL) \
+        BXR_WIN_CASE(8, 4, 1, CALL)                                                        \
+        BXR_WIN_CASE(8, 8, 1, CALL) BXR_WIN_CASE(8, 8, 2, CALL) BXR_WIN_CASE(8, 8, 4, CALL) \
+        BXR_WIN_CASE(16, 8, 1, CALL)                                                       \
+        BXR_WIN_CASE(16, 16, 1, CALL) BXR_WIN_CASE(16, 16, 2, CALL)                        \
+        default: { constexpr int G = 16, SUB = 16, PPL = 4; return CALL; }                 \
     }
 
-int ppl_of(int P, int g) {
-    const int n = (P + g - 1) / g;
-    return n <= 1 ? 1 : (n <= 2 ? 2 : 4);
+int win_key(int P, int g) {
+    int sub = g;
+    if (g >= 8 && P <= g / 2) sub = g / 2;
+    const int n = (P + sub - 1) / sub;
+    const int ppl = n <= 1 ? 1 : (n <= 2 ? 2 : 4);
+    return g * 1000 + sub * 10 + ppl;
 }
 
 template <typename TV>
 int dispatch_fwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(g, ppl_of(p.P, g), (fwd_win<TV, G, PPL>(p, st)))
+    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_win<TV, G, SUB, PPL>(p, st)))
 }
 template <typename TV, typename ACC>
 int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(g, ppl_of(p.P, g), (bwd_win<TV, G, PPL, ACC>(p, st)))
+    BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC>(p, st)))
 }
 
 void fill_sizes(AttnParams& p, int B, int S, int H, int D, int L, int Nq, int P) {

@@ -98,20 +98,62 @@ __device__ __forceinline__ LanePoint lane_point(const float* __restrict__ loc_l,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Forward.  One group of G lanes per row; grid-stride over contiguous blocks of rows.
-template <typename TV, int G, int PPL>
+// Lane geometry shared by the forward and backward kernels.
+//   G    lanes per row (channel slices of 16 bytes)
+//   SUB  lanes that share one level's points (SUB == G: one level per pass; SUB == G/2: two levels
+//        per pass, used for 2x2 grids where P = 4 would leave half of the lanes idle)
+//   PPL  points per lane per level: P <= SUB * PPL
+template <int G, int SUB>
+struct WinGeom {
+    static constexpr int LPP = G / SUB;                  // levels per pass
+    static constexpr int CAP = kWinSlots / LPP;          // window slots per level of a pass
+};
+
+template <int SUB>
+__device__ __forceinline__ int smin(int v, unsigned m) {
+#pragma unroll
+    for (int o = SUB / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(m, v, o));
+    return v;
+}
+template <int SUB>
+__device__ __forceinline__ int smax(int v, unsigned m) {
+#pragma unroll
+    for (int o = SUB / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(m, v, o));
+    return v;
+}
+template <int SUB>
+__device__ __forceinline__ float ssum(float v, unsigned m) {
+#pragma unroll
+    for (int o = SUB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+}
+
+// what every lane of the group needs to know about one level of the current pass
+struct SubWin {
+    int X0, Y0, nx, ny;   // touched pixel range (clamped to the level); nx <= 0: nothing inside
+    int ke;               // fixed-point scale exponent
+    int mode;             // 0 skip, 1 window, 2 per-point fallback
+};
+
+// ------------------------------------------------------------------------------------------------
+// Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
+template <typename TV, int G, int SUB, int PPL>
 __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
+    using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
     constexpr int GROUPS = kThreads / G;
+    constexpr int LPP = GEO::LPP, CAP = GEO::CAP;
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];
     load_levels(lv, p);
 
     const int lane = threadIdx.x % G;
     const int gid = threadIdx.x / G;
+    const int sub = lane / SUB, slane = lane % SUB;          // my level slot of a pass, my lane within it
     const unsigned gm = group_mask<G>();
-    int* win = s_win + gid * kWinPitch;
+    int* gwin = s_win + gid * kWinPitch;
+    int* win = gwin + sub * CAP;
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in 16-byte units
     const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -133,115 +175,140 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
-        for (int l = 0; l < p.L; ++l) {
-            const int lh = lv.h[l], lw = lv.w[l];
-            const unsigned vlev = vrow + (unsigned)lv.start[l] * HDV;
-            // ---- A: own points, touched pixel range
+        for (int l0 = 0; l0 < p.L; l0 += LPP) {
+            // ---- A: own points of my level, touched pixel range (reductions stay inside the SUB lanes)
+            const int lm = l0 + sub;
+            const bool lact = lm < p.L;
+            const int lmc = lact ? lm : 0;
+            const int mh = lv.h[lmc], mw = lv.w[lmc];
             LanePoint pt[PPL];
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
             float S = 0.f;
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
-                pt[k] = lane_point(loc_row + l * p.P * 2, w_row + l * p.P, lane + k * G, p.P, lh, lw);
+                pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, lact ? slane + k * SUB : p.P, p.P, mh, mw);
                 if (pt[k].inside) {
                     bx0 = min(bx0, pt[k].x0); bx1 = max(bx1, pt[k].x0 + 1);
                     by0 = min(by0, pt[k].y0); by1 = max(by1, pt[k].y0 + 1);
                     S += fabsf(pt[k].aw);
                 }
             }
-            const int X0 = max(gmin<G>(bx0, gm), 0), X1 = min(gmax<G>(bx1, gm), lw - 1);
-            const int Y0 = max(gmin<G>(by0, gm), 0), Y1 = min(gmax<G>(by1, gm), lh - 1);
-            const int nx = X1 - X0 + 1, ny = Y1 - Y0 + 1;
-            if (nx <= 0 || ny <= 0) continue;   // no point of this level passed the window test
-            S = gsum<G>(S, gm);
-            if (S == 0.f) continue;             // every weight of this level is exactly zero
+            SubWin me;
+            me.X0 = max(smin<SUB>(bx0, gm), 0); me.Y0 = max(smin<SUB>(by0, gm), 0);
+            me.nx = min(smax<SUB>(bx1, gm), mw - 1) - me.X0 + 1;
+            me.ny = min(smax<SUB>(by1, gm), mh - 1) - me.Y0 + 1;
+            S = ssum<SUB>(S, gm);
+            const int nq = me.nx * me.ny;
+            // non-finite weights (S is NaN/inf) take the float path so that they propagate
+            me.mode = (me.nx <= 0 || me.ny <= 0 || S == 0.f) ? 0 : ((nq <= CAP && S <= 3.0e38f) ? 1 : 2);
+            me.ke = fixed_scale_exp(S);
 
-            // non-finite weights (S is NaN/inf) take the float path below so that they propagate
-            const int nq = nx * ny;
-            if (nq <= kWinSlots && S <= 3.0e38f) {
-                // ---- B: scatter pixel weights into the dense nx x ny window (32-bit fixed point)
-                const int ke = fixed_scale_exp(S);
-                const float scale = pow2f(ke), inv_scale = pow2f(-ke);
-                for (int s = lane; s < ((nq + 3) & ~3); s += G) win[s] = 0;
-                __syncwarp(gm);
+            // ---- B: scatter pixel weights into my level's dense nx x ny window (32-bit fixed point)
+            if (me.mode == 1) {
+                const float scale = pow2f(me.ke);
+                for (int s = slane; s < ((nq + 3) & ~3); s += SUB) win[s] = 0;
+                __syncwarp(gm);                  // (masked __syncwarp tolerates the divergence between sub-groups)
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     if (pt[k].inside) {
-                        const int sx = pt[k].x0 - X0, sy = pt[k].y0 - Y0;   // -1 .. n-1
+                        const int sx = pt[k].x0 - me.X0, sy = pt[k].y0 - me.Y0;   // -1 .. n-1
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
                         const float a = pt[k].aw * scale;
-                        const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
-                        int* wp = win + sy * nx + sx;
+                        const bool vx0 = sx >= 0, vx1 = sx + 1 < me.nx, vy0 = sy >= 0, vy1 = sy + 1 < me.ny;
+                        int* wp = win + sy * me.nx + sx;
                         if (vy0 && vx0) atomicAdd(wp, __float2int_rn(hy * hx * a));
                         if (vy0 && vx1) atomicAdd(wp + 1, __float2int_rn(hy * pt[k].lx * a));
-                        if (vy1 && vx0) atomicAdd(wp + nx, __float2int_rn(pt[k].ly * hx * a));
-                        if (vy1 && vx1) atomicAdd(wp + nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a));
+                        if (vy1 && vx0) atomicAdd(wp + me.nx, __float2int_rn(pt[k].ly * hx * a));
+                        if (vy1 && vx1) atomicAdd(wp + me.nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a));
                     }
                 }
-                __syncwarp(gm);
-                // ---- C: one row load per unique pixel, four window slots at a time; the pixel offset is
-                //         advanced incrementally (no division by nx)
-                const unsigned row_skip = (unsigned)(lw - nx) * HDV;
-                unsigned off = vlev + (unsigned)(Y0 * lw + X0) * HDV;
-                int ix = 0;
-#pragma unroll 2
-                for (int q = 0; q < nq; q += 4) {
-                    const int4 wq = *reinterpret_cast<const int4*>(win + q);
-                    const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
-                    unsigned offs[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        offs[j] = off;
-                        off += HDV;
-                        if (++ix == nx) { ix = 0; off += row_skip; }
-                    }
-                    float v[4][VEC];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (wi[j] != 0) V::load16(value16, offs[j], v[j]);   // slots past nq were zeroed and never written
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (wi[j] != 0) {
-                            const float wv = (float)wi[j] * inv_scale;
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) acc[i] += wv * v[j][i];
-                        }
-                    }
-                }
-                __syncwarp(gm);   // the window is re-zeroed by the next level
             } else {
-                // ---- per-point fallback: owner lane broadcasts its tap
+                __syncwarp(gm);
+            }
+            __syncwarp(gm);
+
+            // ---- C: all G lanes walk the window(s) of this pass
 #pragma unroll
-                for (int k = 0; k < PPL; ++k) {
-                    for (int o = 0; o < G; ++o) {
-                        if (o + k * G >= p.P) break;            // uniform in the group
-                        const bool inside = __shfl_sync(gm, (int)pt[k].inside, o, G) != 0;
-                        const int x0 = __shfl_sync(gm, pt[k].x0, o, G), y0 = __shfl_sync(gm, pt[k].y0, o, G);
-                        const float lx = __shfl_sync(gm, pt[k].lx, o, G), ly = __shfl_sync(gm, pt[k].ly, o, G);
-                        const float aw = __shfl_sync(gm, pt[k].aw, o, G);
-                        if (!inside) continue;
-                        const float hx = 1.f - lx, hy = 1.f - ly;
-                        const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= lw - 1, vy0 = y0 >= 0, vy1 = y0 + 1 <= lh - 1;
-                        const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
-                        const float cw[4] = {hy * hx * aw, hy * lx * aw, ly * hx * aw, ly * lx * aw};
-                        const unsigned c00 = vlev + (unsigned)(y0 * lw + x0) * HDV;   // wraps for x0/y0 = -1; valid corners are right
+            for (int sl = 0; sl < LPP; ++sl) {
+                SubWin w;
+                if (LPP == 1) {
+                    w = me;
+                } else {
+                    const int src = sl * SUB;
+                    w.X0 = __shfl_sync(gm, me.X0, src, G); w.Y0 = __shfl_sync(gm, me.Y0, src, G);
+                    w.nx = __shfl_sync(gm, me.nx, src, G); w.ny = __shfl_sync(gm, me.ny, src, G);
+                    w.ke = __shfl_sync(gm, me.ke, src, G); w.mode = __shfl_sync(gm, me.mode, src, G);
+                }
+                if (w.mode == 0) continue;
+                const int l = l0 + sl;
+                const int lh = lv.h[l], lw = lv.w[l];
+                const unsigned vlev = vrow + (unsigned)lv.start[l] * HDV;
+                if (w.mode == 1) {
+                    // one row load per unique pixel, four window slots at a time; the pixel index is
+                    // advanced incrementally (no division by nx)
+                    const int* cw = gwin + sl * CAP;
+                    const float inv_scale = pow2f(-w.ke);
+                    const int wq_n = w.nx * w.ny;
+                    const unsigned row_skip = (unsigned)(lw - w.nx) * HDV;
+                    unsigned off = vlev + (unsigned)(w.Y0 * lw + w.X0) * HDV;
+                    int ix = 0;
+#pragma unroll 2
+                    for (int q = 0; q < wq_n; q += 4) {
+                        const int4 wq = *reinterpret_cast<const int4*>(cw + q);
+                        const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
+                        unsigned offs[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            offs[j] = off;
+                            off += HDV;
+                            if (++ix == w.nx) { ix = 0; off += row_skip; }
+                        }
                         float v[4][VEC];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (ok[c]) {
-                                V::load16(value16, c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u), v[c]);
-                            } else {
+                        for (int j = 0; j < 4; ++j)
+                            if (wi[j] != 0) V::load16(value16, offs[j], v[j]);   // slots past nq were zeroed and never written
 #pragma unroll
-                                for (int i = 0; i < VEC; ++i) v[c][i] = 0.f;
+                        for (int j = 0; j < 4; ++j) {
+                            if (wi[j] != 0) {
+                                const float wv = (float)wi[j] * inv_scale;
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) acc[i] += wv * v[j][i];
                             }
                         }
+                    }
+                } else {
+                    // per-point fallback: the owner lane broadcasts its tap
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
+                    for (int k = 0; k < PPL; ++k) {
+#pragma unroll 1
+                        for (int o = 0; o < SUB; ++o) {
+                            if (o + k * SUB >= p.P) break;            // uniform in the group
+                            const int src = sl * SUB + o;
+                            const bool inside = __shfl_sync(gm, (int)pt[k].inside, src, G) != 0;
+                            const int x0 = __shfl_sync(gm, pt[k].x0, src, G), y0 = __shfl_sync(gm, pt[k].y0, src, G);
+                            const float lx = __shfl_sync(gm, pt[k].lx, src, G), ly = __shfl_sync(gm, pt[k].ly, src, G);
+                            const float aw = __shfl_sync(gm, pt[k].aw, src, G);
+                            if (!inside) continue;
+                            const float hx = 1.f - lx, hy = 1.f - ly;
+                            const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= lw - 1, vy0 = y0 >= 0, vy1 = y0 + 1 <= lh - 1;
+                            const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
+                            const float cw[4] = {hy * hx * aw, hy * lx * aw, ly * hx * aw, ly * lx * aw};
+                            const unsigned c00 = vlev + (unsigned)(y0 * lw + x0) * HDV;   // wraps for x0/y0 = -1; valid corners are right
+                            float v[4][VEC];
 #pragma unroll
-                            for (int i = 0; i < VEC; ++i) acc[i] += cw[c] * v[c][i];
+                            for (int c = 0; c < 4; ++c)
+                                if (ok[c]) V::load16(value16, c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u), v[c]);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (ok[c]) {
+#pragma unroll
+                                    for (int i = 0; i < VEC; ++i) acc[i] += cw[c] * v[c][i];
+                                }
+                        }
                     }
                 }
             }
+            __syncwarp(gm);   // the windows are re-zeroed by the next pass
         }
         V::store(static_cast<TV*>(p.out) + (row * p.D + lane * VEC), acc);
     }
@@ -287,11 +354,13 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
     return (hi ? 2 : 0) + (lo ? 1 : 0);
 }
 
-template <typename TV, int G, int PPL, typename ACC>
+template <typename TV, int G, int SUB, int PPL, typename ACC>
 __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
+    using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
     constexpr int GROUPS = kThreads / G;
+    constexpr int LPP = GEO::LPP, CAP = GEO::CAP;
     constexpr bool DET = sizeof(ACC) == 8;
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];     // pixel weights W[pix], fixed point
@@ -300,9 +369,12 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
 
     const int lane = threadIdx.x % G;
     const int gid = threadIdx.x / G;
+    const int sub = lane / SUB, slane = lane % SUB;
     const unsigned gm = group_mask<G>();
-    int* win = s_win + gid * kWinPitch;
-    float* dot = s_dot + gid * kWinPitch;
+    int* gwin = s_win + gid * kWinPitch;
+    float* gdot = s_dot + gid * kWinPitch;
+    int* win = gwin + sub * CAP;
+    float* dot = gdot + sub * CAP;
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in 16-byte units
     const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -313,8 +385,6 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
     float dscale = 1.f;
     if constexpr (DET) dscale = *p.det_scale;
 
-    // units are dealt round-robin: rows of the coarse levels (wide windows -> per-point fallback) cost
-    // several times more than level-0 rows, and a contiguous split leaves the CTAs that own them as a tail
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const long long row = (long long)u * GROUPS + gid;
         if (row >= p.rows) continue;
@@ -326,16 +396,18 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
         float go[VEC];
         V::load(static_cast<const TV*>(p.grad_out) + (row * p.D + lane * VEC), go);
 
-        for (int l = 0; l < p.L; ++l) {
-            const int lh = lv.h[l], lw = lv.w[l];
-            const unsigned lbase = vbase + (unsigned)lv.start[l] * HDV;
+        for (int l0 = 0; l0 < p.L; l0 += LPP) {
+            const int lm = l0 + sub;
+            const bool lact = lm < p.L;
+            const int lmc = lact ? lm : 0;
+            const int mh = lv.h[lmc], mw = lv.w[lmc];
             LanePoint pt[PPL];
             float g_a[PPL], g_x[PPL], g_y[PPL];     // this lane's results for its own points
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
             float S = 0.f;
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
-                pt[k] = lane_point(loc_row + l * p.P * 2, w_row + l * p.P, lane + k * G, p.P, lh, lw);
+                pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, lact ? slane + k * SUB : p.P, p.P, mh, mw);
                 g_a[k] = g_x[k] = g_y[k] = 0.f;
                 if (pt[k].inside) {
                     bx0 = min(bx0, pt[k].x0); bx1 = max(bx1, pt[k].x0 + 1);
@@ -343,142 +415,176 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
                     S += fabsf(pt[k].aw);
                 }
             }
-            const int X0 = max(gmin<G>(bx0, gm), 0), X1 = min(gmax<G>(bx1, gm), lw - 1);
-            const int Y0 = max(gmin<G>(by0, gm), 0), Y1 = min(gmax<G>(by1, gm), lh - 1);
-            const int nx = X1 - X0 + 1, ny = Y1 - Y0 + 1;
-            S = gsum<G>(S, gm);
+            SubWin me;
+            me.X0 = max(smin<SUB>(bx0, gm), 0); me.Y0 = max(smin<SUB>(by0, gm), 0);
+            me.nx = min(smax<SUB>(bx1, gm), mw - 1) - me.X0 + 1;
+            me.ny = min(smax<SUB>(by1, gm), mh - 1) - me.Y0 + 1;
+            S = ssum<SUB>(S, gm);
+            const int nq = me.nx * me.ny;
+            me.mode = (me.nx <= 0 || me.ny <= 0) ? 0 : ((nq <= CAP && S <= 3.0e38f) ? 1 : 2);
+            me.ke = fixed_scale_exp(fmaxf(S, 1e-30f));
 
-            const int nq = nx * ny;
-            if (nx > 0 && ny > 0 && nq <= kWinSlots && S <= 3.0e38f) {
-                // B: pixel weights (fixed point) in a dense nx x ny window.  The d window doubles as a
-                //    "touched" flag (1.0) until C overwrites it with the dot products: a pixel touched
-                //    with zero total weight still needs its d.
-                const int ke = fixed_scale_exp(fmaxf(S, 1e-30f));
-                const float scale = pow2f(ke), inv_scale = pow2f(-ke);
-                for (int s = lane; s < ((nq + 3) & ~3); s += G) { win[s] = 0; dot[s] = 0.f; }
+            // B: pixel weights (fixed point) in my level's dense nx x ny window.  The d window doubles as a
+            //    "touched" flag (1.0) until C overwrites it with the dot products: a pixel touched with zero
+            //    total weight still needs its d.
+            if (me.mode == 1) {
+                const float scale = pow2f(me.ke);
+                for (int s = slane; s < ((nq + 3) & ~3); s += SUB) { win[s] = 0; dot[s] = 0.f; }
                 __syncwarp(gm);
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     if (pt[k].inside) {
-                        const int sx = pt[k].x0 - X0, sy = pt[k].y0 - Y0;
+                        const int sx = pt[k].x0 - me.X0, sy = pt[k].y0 - me.Y0;
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
                         const float a = pt[k].aw * scale;
-                        const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
-                        const int s00 = sy * nx + sx;
+                        const bool vx0 = sx >= 0, vx1 = sx + 1 < me.nx, vy0 = sy >= 0, vy1 = sy + 1 < me.ny;
+                        const int s00 = sy * me.nx + sx;
                         if (vy0 && vx0) { atomicAdd(win + s00, __float2int_rn(hy * hx * a)); dot[s00] = 1.f; }
                         if (vy0 && vx1) { atomicAdd(win + s00 + 1, __float2int_rn(hy * pt[k].lx * a)); dot[s00 + 1] = 1.f; }
-                        if (vy1 && vx0) { atomicAdd(win + s00 + nx, __float2int_rn(pt[k].ly * hx * a)); dot[s00 + nx] = 1.f; }
-                        if (vy1 && vx1) { atomicAdd(win + s00 + nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a)); dot[s00 + nx + 1] = 1.f; }
+                        if (vy1 && vx0) { atomicAdd(win + s00 + me.nx, __float2int_rn(pt[k].ly * hx * a)); dot[s00 + me.nx] = 1.f; }
+                        if (vy1 && vx1) { atomicAdd(win + s00 + me.nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a)); dot[s00 + me.nx + 1] = 1.f; }
                     }
                 }
+            } else {
                 __syncwarp(gm);
-                // C: per unique pixel, four window slots at a time:
-                //    value row -> scatter W*go into grad_value, d = <go, v> by transpose reduction
-                const unsigned row_skip = (unsigned)(lw - nx) * HDV;
-                unsigned off = lbase + (unsigned)(Y0 * lw + X0) * HDV;
-                int ix = 0;
-                for (int q = 0; q < nq; q += 4) {
-                    const int4 wq = *reinterpret_cast<const int4*>(win + q);
-                    const float4 tq = *reinterpret_cast<const float4*>(dot + q);
-                    const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
-                    const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
-                    unsigned offs[4];
+            }
+            __syncwarp(gm);
+
+            // C: all G lanes walk the window(s) of this pass
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        offs[j] = off;
-                        off += HDV;
-                        if (++ix == nx) { ix = 0; off += row_skip; }
-                    }
-                    float v[4][VEC];
+            for (int sl = 0; sl < LPP; ++sl) {
+                SubWin w;
+                if (LPP == 1) {
+                    w = me;
+                } else {
+                    const int src = sl * SUB;
+                    w.X0 = __shfl_sync(gm, me.X0, src, G); w.Y0 = __shfl_sync(gm, me.Y0, src, G);
+                    w.nx = __shfl_sync(gm, me.nx, src, G); w.ny = __shfl_sync(gm, me.ny, src, G);
+                    w.ke = __shfl_sync(gm, me.ke, src, G); w.mode = __shfl_sync(gm, me.mode, src, G);
+                }
+                if (w.mode == 0) continue;
+                const int l = l0 + sl;
+                const int lh = lv.h[l], lw = lv.w[l];
+                const unsigned lbase = vbase + (unsigned)lv.start[l] * HDV;
+                if (w.mode == 1) {
+                    // per unique pixel, four window slots at a time:
+                    // value row -> scatter W*go into grad_value, d = <go, v> by transpose reduction
+                    const int* cwin = gwin + sl * CAP;
+                    float* cdot = gdot + sl * CAP;
+                    const float inv_scale = pow2f(-w.ke);
+                    const int wq_n = w.nx * w.ny;
+                    const unsigned row_skip = (unsigned)(lw - w.nx) * HDV;
+                    unsigned off = lbase + (unsigned)(w.Y0 * lw + w.X0) * HDV;
+                    int ix = 0;
+                    for (int q = 0; q < wq_n; q += 4) {
+                        const int4 wq = *reinterpret_cast<const int4*>(cwin + q);
+                        const float4 tq = *reinterpret_cast<const float4*>(cdot + q);
+                        const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
+                        const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                        unsigned offs[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (tv[j] != 0.f) {        // slots past nq were zeroed and never flagged
-                            V::load16(value16, offs[j], v[j]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
+                        for (int j = 0; j < 4; ++j) {
+                            offs[j] = off;
+                            off += HDV;
+                            if (++ix == w.nx) { ix = 0; off += row_skip; }
                         }
-                    }
-                    float dsum[4];
+                        float v[4][VEC];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float t = 0.f;
+                        for (int j = 0; j < 4; ++j) {
+                            if (tv[j] != 0.f) {        // slots past nq were zeroed and never flagged
+                                V::load16(value16, offs[j], v[j]);
+                            } else {
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
-                        dsum[j] = t;
-                        if (wi[j] != 0) scatter_row<ACC, VEC>(gacc + (size_t)offs[j] * VEC, go, (float)wi[j] * inv_scale, dscale);
-                    }
-                    float total;
-                    const int mine = reduce4<G>(dsum, total, lane, gm);   // also orders the flag reads before the writes
-                    dot[q + mine] = total;                                 // lanes sharing an index write the same value
-                }
-                __syncwarp(gm);
-                // D: finish own points from the d window
-#pragma unroll
-                for (int k = 0; k < PPL; ++k) {
-                    if (pt[k].inside) {
-                        const int sx = pt[k].x0 - X0, sy = pt[k].y0 - Y0;
-                        const float lx = pt[k].lx, ly = pt[k].ly, hx = 1.f - lx, hy = 1.f - ly;
-                        const bool vx0 = sx >= 0, vx1 = sx + 1 < nx, vy0 = sy >= 0, vy1 = sy + 1 < ny;
-                        const int s00 = sy * nx + sx;
-                        const float d00 = (vy0 && vx0) ? dot[s00] : 0.f;
-                        const float d01 = (vy0 && vx1) ? dot[s00 + 1] : 0.f;
-                        const float d10 = (vy1 && vx0) ? dot[s00 + nx] : 0.f;
-                        const float d11 = (vy1 && vx1) ? dot[s00 + nx + 1] : 0.f;
-                        g_a[k] = hy * hx * d00 + hy * lx * d01 + ly * hx * d10 + ly * lx * d11;
-                        g_x[k] = (float)lw * pt[k].aw * (hy * (d01 - d00) + ly * (d11 - d10));
-                        g_y[k] = (float)lh * pt[k].aw * (hx * (d10 - d00) + lx * (d11 - d01));
-                    }
-                }
-                __syncwarp(gm);
-            } else if (nx > 0 && ny > 0) {
-                // per-point fallback (window too large, or non-finite weights)
-#pragma unroll
-                for (int k = 0; k < PPL; ++k) {
-                    for (int o = 0; o < G; ++o) {
-                        if (o + k * G >= p.P) break;
-                        const bool inside = __shfl_sync(gm, (int)pt[k].inside, o, G) != 0;
-                        const int x0 = __shfl_sync(gm, pt[k].x0, o, G), y0 = __shfl_sync(gm, pt[k].y0, o, G);
-                        const float lx = __shfl_sync(gm, pt[k].lx, o, G), ly = __shfl_sync(gm, pt[k].ly, o, G);
-                        const float aw = __shfl_sync(gm, pt[k].aw, o, G);
-                        if (!inside) continue;
-                        const float hx = 1.f - lx, hy = 1.f - ly;
-                        const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= lw - 1, vy0 = y0 >= 0, vy1 = y0 + 1 <= lh - 1;
-                        const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
-                        const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
-                        const unsigned c00 = lbase + (unsigned)(y0 * lw + x0) * HDV;
-                        float d[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float s = 0.f;
-                            if (ok[c]) {
-                                const unsigned off = c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u);
-                                float v[VEC];
-                                V::load16(value16, off, v);
-#pragma unroll
-                                for (int i = 0; i < VEC; ++i) s += go[i] * v[i];
-                                scatter_row<ACC, VEC>(gacc + (size_t)off * VEC, go, cw[c] * aw, dscale);
+                                for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
                             }
-                            d[c] = s;
                         }
+                        float dsum[4];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) d[c] = gsum<G>(d[c], gm);
-                        if (lane == o) {
-                            g_a[k] = cw[0] * d[0] + cw[1] * d[1] + cw[2] * d[2] + cw[3] * d[3];
-                            g_x[k] = (float)lw * aw * (hy * (d[1] - d[0]) + ly * (d[3] - d[2]));
-                            g_y[k] = (float)lh * aw * (hx * (d[2] - d[0]) + lx * (d[3] - d[1]));
+                        for (int j = 0; j < 4; ++j) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
+                            dsum[j] = t;
+                            if (wi[j] != 0) scatter_row<ACC, VEC>(gacc + (size_t)offs[j] * VEC, go, (float)wi[j] * inv_scale, dscale);
+                        }
+                        float total;
+                        const int mine = reduce4<G>(dsum, total, lane, gm);   // also orders the flag reads before the writes
+                        cdot[q + mine] = total;                                // lanes sharing an index write the same value
+                    }
+                } else {
+                    // per-point fallback (window too large, or non-finite weights)
+#pragma unroll
+                    for (int k = 0; k < PPL; ++k) {
+#pragma unroll 1
+                        for (int o = 0; o < SUB; ++o) {
+                            if (o + k * SUB >= p.P) break;
+                            const int src = sl * SUB + o;
+                            const bool inside = __shfl_sync(gm, (int)pt[k].inside, src, G) != 0;
+                            const int x0 = __shfl_sync(gm, pt[k].x0, src, G), y0 = __shfl_sync(gm, pt[k].y0, src, G);
+                            const float lx = __shfl_sync(gm, pt[k].lx, src, G), ly = __shfl_sync(gm, pt[k].ly, src, G);
+                            const float aw = __shfl_sync(gm, pt[k].aw, src, G);
+                            if (!inside) continue;
+                            const float hx = 1.f - lx, hy = 1.f - ly;
+                            const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= lw - 1, vy0 = y0 >= 0, vy1 = y0 + 1 <= lh - 1;
+                            const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
+                            const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+                            const unsigned c00 = lbase + (unsigned)(y0 * lw + x0) * HDV;
+                            float d[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                float t = 0.f;
+                                if (ok[c]) {
+                                    const unsigned off = c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u);
+                                    float v[VEC];
+                                    V::load16(value16, off, v);
+#pragma unroll
+                                    for (int i = 0; i < VEC; ++i) t += go[i] * v[i];
+                                    scatter_row<ACC, VEC>(gacc + (size_t)off * VEC, go, cw[c] * aw, dscale);
+                                }
+                                d[c] = t;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) d[c] = gsum<G>(d[c], gm);
+                            if (lane == src) {
+                                g_a[k] = cw[0] * d[0] + cw[1] * d[1] + cw[2] * d[2] + cw[3] * d[3];
+                                g_x[k] = (float)lw * aw * (hy * (d[1] - d[0]) + ly * (d[3] - d[2]));
+                                g_y[k] = (float)lh * aw * (hx * (d[2] - d[0]) + lx * (d[3] - d[1]));
+                            }
                         }
                     }
                 }
             }
-            // coalesced stores of this level's gradients (zeros for points outside the window test)
+            __syncwarp(gm);
+            // D: finish own points from the d window of my level
+            if (me.mode == 1) {
 #pragma unroll
-            for (int k = 0; k < PPL; ++k) {
-                const int ptn = lane + k * G;
-                if (ptn < p.P) {
-                    const long long s = row * p.LP + (long long)l * p.P + ptn;
-                    grad_w0[s] = g_a[k];
-                    reinterpret_cast<float2*>(grad_loc)[s] = make_float2(g_x[k], g_y[k]);
+                for (int k = 0; k < PPL; ++k) {
+                    if (pt[k].inside) {
+                        const int sx = pt[k].x0 - me.X0, sy = pt[k].y0 - me.Y0;
+                        const float lx = pt[k].lx, ly = pt[k].ly, hx = 1.f - lx, hy = 1.f - ly;
+                        const bool vx0 = sx >= 0, vx1 = sx + 1 < me.nx, vy0 = sy >= 0, vy1 = sy + 1 < me.ny;
+                        const int s00 = sy * me.nx + sx;
+                        const float d00 = (vy0 && vx0) ? dot[s00] : 0.f;
+                        const float d01 = (vy0 && vx1) ? dot[s00 + 1] : 0.f;
+                        const float d10 = (vy1 && vx0) ? dot[s00 + me.nx] : 0.f;
+                        const float d11 = (vy1 && vx1) ? dot[s00 + me.nx + 1] : 0.f;
+                        g_a[k] = hy * hx * d00 + hy * lx * d01 + ly * hx * d10 + ly * lx * d11;
+                        g_x[k] = (float)mw * pt[k].aw * (hy * (d01 - d00) + ly * (d11 - d10));
+                        g_y[k] = (float)mh * pt[k].aw * (hx * (d10 - d00) + lx * (d11 - d01));
+                    }
+                }
+            }
+            __syncwarp(gm);
+            // coalesced stores of this pass's gradients (zeros for points outside the window test)
+            if (lact) {
+#pragma unroll
+                for (int k = 0; k < PPL; ++k) {
+                    const int ptn = slane + k * SUB;
+                    if (ptn < p.P) {
+                        const long long s = row * p.LP + (long long)lm * p.P + ptn;
+                        grad_w0[s] = g_a[k];
+                        reinterpret_cast<float2*>(grad_loc)[s] = make_float2(g_x[k], g_y[k]);
+                    }
                 }
             }
         }
