@@ -17,7 +17,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "_C")
-LIB_PATH = os.path.join(LIB_DIR, "libboxattn_b200.so")
+# BOXER_B200_LIB: experiment hook (A/B builds of the same ABI); the default is the in-tree build
+LIB_PATH = os.environ.get("BOXER_B200_LIB") or os.path.join(LIB_DIR, "libboxattn_b200.so")
 HEADER = os.path.join(ROOT, "include", "boxattn_b200.h")
 SOURCES = [os.path.join(CSRC, "boxattn_abi.cu")]
 DEPENDS = SOURCES + [os.path.join(CSRC, "boxattn_kernels.cuh"), os.path.join(CSRC, "boxattn_fused.cuh"), HEADER]

@@ -28,6 +28,19 @@
 
 namespace bxr {
 
+// resident CTAs per SM the fp32 window kernels are compiled for (A/B measured on B200, profiles/README.md):
+// forward 3 (<= 80 registers, no spills), backward 4 (<= 64 registers)
+#ifndef BXR_FWD_MINB
+#define BXR_FWD_MINB 3
+#endif
+#ifndef BXR_BWD_MINB
+#define BXR_BWD_MINB 4
+#endif
+#ifndef BXR_FB_UNROLL
+#define BXR_FB_UNROLL 1   // unroll factor of the per-point fallback loop
+#endif
+
+constexpr int kFbUnroll = BXR_FB_UNROLL;
 constexpr int kWinSide = 8;
 constexpr int kWinSlots = kWinSide * kWinSide;
 // per-group pitch of a window in 32-bit words: 64 slots + 4 words of skew, so that the 16-byte
@@ -138,7 +151,7 @@ struct SubWin {
 // ------------------------------------------------------------------------------------------------
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
 template <typename TV, int G, int SUB, int PPL>
-__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_FWD_MINB) box_fwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 4) box_fwd_w
                     // per-point fallback: the owner lane broadcasts its tap
 #pragma unroll
                     for (int k = 0; k < PPL; ++k) {
-#pragma unroll 1
+#pragma unroll kFbUnroll
                         for (int o = 0; o < SUB; ++o) {
                             if (o + k * SUB >= p.P) break;            // uniform in the group
                             const int src = sl * SUB + o;
@@ -355,7 +368,7 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
 }
 
 template <typename TV, int G, int SUB, int PPL, typename ACC>
-__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB) box_bwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
@@ -515,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : 3) box_bwd_w
                     // per-point fallback (window too large, or non-finite weights)
 #pragma unroll
                     for (int k = 0; k < PPL; ++k) {
-#pragma unroll 1
+#pragma unroll kFbUnroll
                         for (int o = 0; o < SUB; ++o) {
                             if (o + k * SUB >= p.P) break;
                             const int src = sl * SUB + o;
