@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(_PKG, "_C")
 LIB_PATH = os.environ.get("BOXER_B200_LIB") or os.path.join(LIB_DIR, "libboxattn_b200.so")
 HEADER = os.path.join(ROOT, "include", "boxattn_b200.h")
 SOURCES = [os.path.join(CSRC, "boxattn_abi.cu")]
-DEPENDS = SOURCES + [os.path.join(CSRC, "boxattn_kernels.cuh"), os.path.join(CSRC, "boxattn_fused.cuh"), HEADER]
+DEPENDS = SOURCES + [os.path.join(CSRC, "boxattn_kernels.cuh"), os.path.join(CSRC, "boxattn_window.cuh"), os.path.join(CSRC, "boxattn_instance.cuh"), HEADER]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

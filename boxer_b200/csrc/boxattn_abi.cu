@@ -10,6 +10,7 @@
 
 #include "boxattn_kernels.cuh"
 #include "boxattn_window.cuh"
+#include "boxattn_instance.cuh"
 #include "../../include/boxattn_b200.h"
 
 namespace {
@@ -211,6 +212,39 @@ int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st) {
     BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC>(p, st)))
 }
 
+// ---- owner-tap instance kernels (boxattn_instance.cuh)
+constexpr int kInstLevels = 4;
+bool use_inst_own(const AttnParams& p, int g, unsigned flags) {
+    if (flags & BXR_FLAG_PATH_POINT) return false;
+    if (g != 4 && g != 8) return false;
+    if (p.L > kInstLevels || p.P < 1) return false;
+    if ((long long)p.B * p.S * g * p.H >= 0xffffffffLL) return false;
+    return true;
+}
+
+// split a row's point chunks (G points each) over 2^k groups of a CTA until the GPU is filled
+void choose_chunk_split(AttnParams& p, int G) {
+    const int groups = kThreads / G;
+    const int nchunks = (p.P + G - 1) / G;
+    const long long want_units = 4LL * sm_count();
+    int k = 0;
+    while ((1 << (k + 1)) <= groups && (1 << (k + 1)) <= nchunks && (p.rows << k) / groups < want_units) ++k;
+    p.nsplit_log2 = k;
+    const int rows_per_unit = groups >> k;
+    p.units = (int)((p.rows + rows_per_unit - 1) / rows_per_unit);
+}
+
+template <typename TV, int G>
+int fwd_inst_own(AttnParams& p, cudaStream_t st) {
+    choose_chunk_split(p, G);
+    return launch_units<inst_fwd_own_kernel<TV, G, kInstLevels>>(p, st, "inst_fwd_own_kernel");
+}
+template <typename TV, int G, typename ACC>
+int bwd_inst_own(AttnParams& p, cudaStream_t st) {
+    choose_chunk_split(p, G);
+    return launch_units<inst_bwd_own_kernel<TV, G, kInstLevels, ACC>>(p, st, "inst_bwd_own_kernel");
+}
+
 void fill_sizes(AttnParams& p, int B, int S, int H, int D, int L, int Nq, int P) {
     p.B = B; p.S = S; p.H = H; p.D = D; p.L = L; p.Nq = Nq; p.P = P;
     p.LP = L * P;
@@ -248,6 +282,8 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
         if constexpr (!std::is_same<TV, double>::value) {
             if constexpr (!INSTANCE) {
                 if (use_window(p, g, flags)) return dispatch_fwd_win<TV>(g, p, st);
+            } else {
+                if (use_inst_own(p, g, flags)) return g == 8 ? fwd_inst_own<TV, 8>(p, st) : fwd_inst_own<TV, 4>(p, st);
             }
             return dispatch_fwd_vec<TV, INSTANCE>(g, p, st);
         }
@@ -356,9 +392,16 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
     if constexpr (!std::is_same<TV, double>::value) {
         bool win = false;
         if constexpr (!INSTANCE) win = vec_ok && use_window(p, g, flags);
+        bool own = false;
+        if constexpr (INSTANCE) own = vec_ok && use_inst_own(p, g, flags);
         if (win) {
             if constexpr (!INSTANCE)
                 status = det ? dispatch_bwd_win<TV, long long>(g, p, st) : dispatch_bwd_win<TV, float>(g, p, st);
+        } else if (own) {
+            if constexpr (INSTANCE) {
+                if (g == 8) status = det ? bwd_inst_own<TV, 8, long long>(p, st) : bwd_inst_own<TV, 8, float>(p, st);
+                else status = det ? bwd_inst_own<TV, 4, long long>(p, st) : bwd_inst_own<TV, 4, float>(p, st);
+            }
         } else if (vec_ok) {
             status = det ? dispatch_bwd_vec<TV, INSTANCE, long long>(g, p, st) : dispatch_bwd_vec<TV, INSTANCE, float>(g, p, st);
         } else {

@@ -1,0 +1,285 @@
+// Instance attention (the mask head: a K x K RoI grid per query, two weights per point and a
+// per-point "mask" output -- reference: instance_attn_kernel.cuh:98-187, 282-364) with
+// owner-computed taps.
+//
+// The point kernels of boxattn_kernels.cuh derive every tap on all G lanes of a row.  Here the
+// G lanes of a group take G consecutive points of the row: each lane computes the taps of ITS point
+// for all levels once (coalesced location / weight loads), then the group walks the G points and
+// every lane receives the current point's tap by shuffle, fetches its 16-byte slice of the four
+// corner rows and accumulates
+//     out      += spatial_w * val                (reduced over the row's point splits through smem)
+//     mask[p]  += level_w  * val   over levels   (one 16-byte store per lane per point)
+// Backward: the same walk with the scatter to grad_value (red.v4 / fixed point), and the four
+// per-point reductions (d spatial_w, d level_w, d x, d y) handed back to the owner lane, which
+// writes its point's gradients coalesced after the walk.
+#pragma once
+
+#include "boxattn_kernels.cuh"
+#include "boxattn_window.cuh"
+
+namespace bxr {
+
+// tap of one (point, level) as broadcast to the whole group
+struct BTap {
+    bool inside;
+    int x0, y0;
+    float lx, ly, sw, lw;
+};
+
+template <int G>
+__device__ __forceinline__ BTap bcast_tap(const LanePoint& t, float lw, int src, unsigned gm) {
+    BTap b;
+    b.inside = __shfl_sync(gm, (int)t.inside, src, G) != 0;
+    b.x0 = __shfl_sync(gm, t.x0, src, G);
+    b.y0 = __shfl_sync(gm, t.y0, src, G);
+    b.lx = __shfl_sync(gm, t.lx, src, G);
+    b.ly = __shfl_sync(gm, t.ly, src, G);
+    b.sw = __shfl_sync(gm, t.aw, src, G);
+    b.lw = __shfl_sync(gm, lw, src, G);
+    return b;
+}
+
+// LB: levels held in registers per lane (L <= LB)
+template <typename TV, int G, int LB>
+__global__ void __launch_bounds__(kThreads, 2) inst_fwd_own_kernel(const AttnParams p) {
+    using V = Vec16<TV>;
+    constexpr int VEC = V::VEC;
+    constexpr int GROUPS = kThreads / G;
+    __shared__ LevelTable lv;
+    __shared__ float s_red[kThreads * VEC];
+    load_levels(lv, p);
+
+    const int lane = threadIdx.x % G;
+    const int gid = threadIdx.x / G;
+    const unsigned gm = group_mask<G>();
+    const int nsplit = 1 << p.nsplit_log2;
+    const int rows_per_unit = GROUPS >> p.nsplit_log2;
+    const int r_local = gid >> p.nsplit_log2;
+    const int split = gid & (nsplit - 1);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;
+    const long long HD = (long long)p.H * p.D;
+    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
+    const float* __restrict__ loc = static_cast<const float*>(p.loc);
+    const float* __restrict__ w0 = static_cast<const float*>(p.w0);
+    const float* __restrict__ w1 = static_cast<const float*>(p.w1);
+    const int nchunks = (p.P + G - 1) / G;
+
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const long long row = (long long)u * rows_per_unit + r_local;
+        const bool row_ok = row < p.rows;
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+        if (row_ok) {
+            const int head = (int)(row % p.H);
+            const long long bq = row / p.H;
+            const long long b = bq / p.Nq;
+            const unsigned vrow = (unsigned)(b * p.S * HDV + head * G + lane);
+            const float* loc_row = loc + row * p.LP * 2;
+            const float* sw_row = w0 + row * p.LP;
+            const float* lw_row = w1 + row * p.LP;
+            TV* mrow = static_cast<TV*>(p.mask_out) + (bq * p.P * HD + (long long)head * p.D + lane * VEC);
+
+            for (int c = split; c < nchunks; c += nsplit) {
+                const int p0 = c * G;
+                const int pm = p0 + lane;
+                // ---- my point's taps for every level
+                LanePoint tp[LB];
+                float lwv[LB];
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    if (l < p.L) {
+                        tp[l] = lane_point(loc_row + l * p.P * 2, sw_row + l * p.P, pm, p.P, lv.h[l], lv.w[l]);
+                        lwv[l] = pm < p.P ? __ldg(lw_row + l * p.P + pm) : 0.f;
+                    } else {
+                        tp[l].inside = false; tp[l].x0 = tp[l].y0 = 0; tp[l].lx = tp[l].ly = tp[l].aw = 0.f;
+                        lwv[l] = 0.f;
+                    }
+                }
+                const int n_here = min(G, p.P - p0);
+                // ---- walk the points of the chunk
+#pragma unroll 1
+                for (int o = 0; o < n_here; ++o) {
+                    float macc[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) macc[i] = 0.f;
+#pragma unroll
+                    for (int l = 0; l < LB; ++l) {
+                        if (l >= p.L) break;
+                        const BTap t = bcast_tap<G>(tp[l], lwv[l], o, gm);
+                        if (!t.inside) continue;
+                        const int lh = lv.h[l], lw = lv.w[l];
+                        const float hx = 1.f - t.lx, hy = 1.f - t.ly;
+                        const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= lw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
+                        const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
+                        const float cw[4] = {hy * hx, hy * t.lx, t.ly * hx, t.ly * t.lx};
+                        const unsigned c00 = vrow + ((unsigned)lv.start[l] + (unsigned)(t.y0 * lw + t.x0)) * HDV;
+                        float v[4][VEC];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (ok[k]) {
+                                V::load16(value16, c00 + ((k & 1) ? HDV : 0u) + ((k & 2) ? (unsigned)lw * HDV : 0u), v[k]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) v[k][i] = 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            const float val = cw[0] * v[0][i] + cw[1] * v[1][i] + cw[2] * v[2][i] + cw[3] * v[3][i];
+                            acc[i] += val * t.sw;       // instance_attn_kernel.cuh:354
+                            macc[i] += val * t.lw;      // :355
+                        }
+                    }
+                    V::store(mrow + (long long)(p0 + o) * HD, macc);
+                }
+            }
+        }
+
+        TV* orow = static_cast<TV*>(p.out) + (row * p.D + lane * VEC);
+        if (nsplit == 1) {
+            if (row_ok) V::store(orow, acc);
+        } else {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s_red[threadIdx.x * VEC + i] = acc[i];
+            __syncthreads();
+            if (split == 0 && row_ok) {
+                for (int s = 1; s < nsplit; ++s)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[i] += s_red[(threadIdx.x + s * G) * VEC + i];
+                V::store(orow, acc);
+            }
+        }
+    }
+}
+
+template <typename TV, int G, int LB, typename ACC>
+__global__ void __launch_bounds__(kThreads, 2) inst_bwd_own_kernel(const AttnParams p) {
+    using V = Vec16<TV>;
+    constexpr int VEC = V::VEC;
+    constexpr int GROUPS = kThreads / G;
+    constexpr bool DET = sizeof(ACC) == 8;
+    __shared__ LevelTable lv;
+    load_levels(lv, p);
+
+    const int lane = threadIdx.x % G;
+    const int gid = threadIdx.x / G;
+    const unsigned gm = group_mask<G>();
+    const int nsplit = 1 << p.nsplit_log2;
+    const int rows_per_unit = GROUPS >> p.nsplit_log2;
+    const int r_local = gid >> p.nsplit_log2;
+    const int split = gid & (nsplit - 1);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;
+    const long long HD = (long long)p.H * p.D;
+    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
+    const float* __restrict__ loc = static_cast<const float*>(p.loc);
+    const float* __restrict__ w0 = static_cast<const float*>(p.w0);
+    const float* __restrict__ w1 = static_cast<const float*>(p.w1);
+    ACC* __restrict__ gacc = static_cast<ACC*>(p.grad_value_acc);
+    float* __restrict__ grad_loc = static_cast<float*>(p.grad_loc);
+    float* __restrict__ grad_w0 = static_cast<float*>(p.grad_w0);
+    float* __restrict__ grad_w1 = static_cast<float*>(p.grad_w1);
+    const int nchunks = (p.P + G - 1) / G;
+    float dscale = 1.f;
+    if constexpr (DET) dscale = *p.det_scale;
+
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const long long row = (long long)u * rows_per_unit + r_local;
+        if (row >= p.rows) continue;               // no block-wide barrier in this kernel
+        const int head = (int)(row % p.H);
+        const long long bq = row / p.H;
+        const long long b = bq / p.Nq;
+        const unsigned vrow = (unsigned)(b * p.S * HDV + head * G + lane);
+        const float* loc_row = loc + row * p.LP * 2;
+        const float* sw_row = w0 + row * p.LP;
+        const float* lw_row = w1 + row * p.LP;
+        const TV* gmrow = static_cast<const TV*>(p.grad_mask) + (bq * p.P * HD + (long long)head * p.D + lane * VEC);
+        float go[VEC];
+        V::load(static_cast<const TV*>(p.grad_out) + (row * p.D + lane * VEC), go);
+
+        for (int c = split; c < nchunks; c += nsplit) {
+            const int p0 = c * G;
+            const int pm = p0 + lane;
+            LanePoint tp[LB];
+            float lwv[LB];
+            float r_s[LB], r_l[LB], r_x[LB], r_y[LB];      // my point's gradients, per level
+#pragma unroll
+            for (int l = 0; l < LB; ++l) {
+                r_s[l] = r_l[l] = r_x[l] = r_y[l] = 0.f;
+                if (l < p.L) {
+                    tp[l] = lane_point(loc_row + l * p.P * 2, sw_row + l * p.P, pm, p.P, lv.h[l], lv.w[l]);
+                    lwv[l] = pm < p.P ? __ldg(lw_row + l * p.P + pm) : 0.f;
+                } else {
+                    tp[l].inside = false; tp[l].x0 = tp[l].y0 = 0; tp[l].lx = tp[l].ly = tp[l].aw = 0.f;
+                    lwv[l] = 0.f;
+                }
+            }
+            const int n_here = min(G, p.P - p0);
+#pragma unroll 1
+            for (int o = 0; o < n_here; ++o) {
+                float gmv[VEC];
+                V::load(gmrow + (long long)(p0 + o) * HD, gmv);
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    if (l >= p.L) break;
+                    const BTap t = bcast_tap<G>(tp[l], lwv[l], o, gm);
+                    if (!t.inside) continue;
+                    const int lh = lv.h[l], lw = lv.w[l];
+                    const float hx = 1.f - t.lx, hy = 1.f - t.ly;
+                    const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= lw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
+                    const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
+                    const float cw[4] = {hy * hx, hy * t.lx, t.ly * hx, t.ly * t.lx};
+                    const unsigned c00 = vrow + ((unsigned)lv.start[l] + (unsigned)(t.y0 * lw + t.x0)) * HDV;
+                    float tg[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) tg[i] = go[i] * t.sw + gmv[i] * t.lw;    // instance_attn_kernel.cuh:139
+                    float v[4][VEC];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned off = c00 + ((k & 1) ? HDV : 0u) + ((k & 2) ? (unsigned)lw * HDV : 0u);
+                        if (ok[k]) {
+                            V::load16(value16, off, v[k]);
+                            scatter_row<ACC, VEC>(gacc + (size_t)off * VEC, tg, cw[k], dscale);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) v[k][i] = 0.f;
+                        }
+                    }
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};    // d spatial_w, d level_w, d x, d y (partials over my channels)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float val = cw[0] * v[0][i] + cw[1] * v[1][i] + cw[2] * v[2][i] + cw[3] * v[3][i];
+                        d[0] += go[i] * val;                                                  // :183
+                        d[1] += gmv[i] * val;                                                 // :184
+                        d[2] += (hy * (v[1][i] - v[0][i]) + t.ly * (v[3][i] - v[2][i])) * tg[i];
+                        d[3] += (hx * (v[2][i] - v[0][i]) + t.lx * (v[3][i] - v[1][i])) * tg[i];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) d[k] = gsum<G>(d[k], gm);
+                    if (lane == o) {
+                        r_s[l] = d[0];
+                        r_l[l] = d[1];
+                        r_x[l] = (float)lw * d[2];
+                        r_y[l] = (float)lh * d[3];
+                    }
+                }
+            }
+            // my point's gradients, coalesced over the lanes of the group (zeros where the sample was outside)
+            if (pm < p.P) {
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    if (l < p.L) {
+                        const long long s = row * p.LP + (long long)l * p.P + pm;
+                        grad_w0[s] = r_s[l];
+                        grad_w1[s] = r_l[l];
+                        reinterpret_cast<float2*>(grad_loc)[s] = make_float2(r_x[l], r_y[l]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace bxr

@@ -188,7 +188,7 @@ def instance_attn_forward(value, spatial_shapes, level_start_index, sampling_loc
         st = getattr(lib, f"bxr_instance_attn_fwd_{suf}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), spatial_attn_weight.data_ptr(), level_attn_weight.data_ptr(),
-            B, S, H, D, L, Nq, P, out.data_ptr(), mask_out.data_ptr(), 0, _stream(value.device))
+            B, S, H, D, L, Nq, P, out.data_ptr(), mask_out.data_ptr(), _PATH_FLAGS, _stream(value.device))
     _native.check(st, "instance_attn_forward")
     return [out, mask_out]
 
@@ -206,7 +206,7 @@ def instance_attn_backward(value, spatial_shapes, level_start_index, sampling_lo
         raise RuntimeError("grad_mask_output must match the forward mask output's dtype and size")
     _step_check(B, im2col_step)
     lib = _native.load()
-    flags = FLAG_DETERMINISTIC if deterministic() else 0
+    flags = (FLAG_DETERMINISTIC if deterministic() else 0) | _PATH_FLAGS
     grad_value = torch.empty_like(value)
     grad_loc = torch.empty_like(sampling_loc)
     grad_sw = torch.empty_like(spatial_attn_weight)
