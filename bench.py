@@ -45,6 +45,16 @@ CFG = dict(workload="BoxeR-2D encoder box-attn: 4 FPN levels (100x167,50x84,25x4
            B_per_gpu=1, K=4, heads=8, head_dim=32, levels=4, Nq=22223, dist="box")
 
 
+def ncu_traffic():
+    """Measured DRAM bytes per launch of the two kernels, from the committed ncu capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get("fwd_bytes"), t.get("bwd_bytes"), t.get("source")
+    except Exception:
+        return None, None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -453,6 +463,7 @@ def main():
     ach_b = n_samples * bb / (kb_ms * 1e-3) / 1e9
     ach_s = n_samples * (bf + bb) / ((kf_ms + kb_ms) * 1e-3) / 1e9
 
+    tr_f, tr_b, tr_src = ncu_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -461,10 +472,11 @@ def main():
                        l2="working set ~364 MB/step (> 126 MB L2); 2 rotating input sets; no explicit flush",
                        locations="box-structured (encoder reference windows + init-state offsets), see boxer_b200/workloads.py"),
         "roofline": {"bound": "hbm", "kernel": "box_bwd_win_kernel<float,G=8,SUB=8,PPL=2,atomic> (+ grad_value memset)",
-                     "achieved": ach_b, "peak": bw_peak, "unit": "GB/s", "frac": ach_b / bw_peak, "traffic": None,
+                     "achieved": ach_b, "peak": bw_peak, "unit": "GB/s", "frac": ach_b / bw_peak, "traffic": tr_b,
+                     "traffic_source": tr_src, "algorithmic_bytes": n_samples * bb,
                      "peak_source": peak_src, "bytes_per_sample": bb, "ms_per_launch": kb_ms},
         "roofline_fwd": {"bound": "hbm", "kernel": "box_fwd_win_kernel<float,G=8,SUB=8,PPL=2>", "achieved": ach_f, "peak": bw_peak,
-                         "unit": "GB/s", "frac": ach_f / bw_peak, "traffic": None, "bytes_per_sample": bf,
+                         "unit": "GB/s", "frac": ach_f / bw_peak, "traffic": tr_f, "algorithmic_bytes": n_samples * bf, "bytes_per_sample": bf,
                          "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6},
         "roofline_step": {"achieved": ach_s, "frac": ach_s / bw_peak, "unit": "GB/s"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
