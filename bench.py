@@ -388,6 +388,27 @@ def variants(ops, dev, bw_peak):
     tb = time_call(lambda: ops.box_attn_backward(w.value, w.shapes, w.level_start, w.loc, w.weights[0], go, 64), reps=5)
     ops.set_deterministic(None)
     res["enc_K4_box_f32_deterministic"] = {"bwd_ms": tb}
+
+    # warm vs L2-flushed: one launch at a time, a 512 MB write in between evicts value / loc from L2
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def cold(fn, reps=10):
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    a0 = (w.value, w.shapes, w.level_start, w.loc, w.weights[0])
+    res["enc_K4_box_f32_L2_flushed"] = {
+        "fwd_ms": cold(lambda: ops.box_attn_forward(*a0, 64)),
+        "bwd_ms": cold(lambda: ops.box_attn_backward(*a0, go, 64)),
+        "note": "median of 10 single launches, each after a 512 MB fill (L2 flushed); compare enc_K4_box_f32 (back-to-back)"}
     return res
 
 
@@ -503,7 +524,7 @@ def main():
         with open(os.path.join(ROOT, "gpurun_out", "variants.json"), "w") as f:
             json.dump(v, f, indent=1)
         for k, r in v.items():
-            print(k, {a: round(b, 4) for a, b in r.items()}, file=sys.stderr)
+            print(k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in r.items()}, file=sys.stderr)
 
     if rank == 0:
         print(json.dumps(line))

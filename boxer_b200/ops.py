@@ -126,6 +126,38 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+class _on_device:
+    """Device guard that costs nothing when the tensors already live on the current device
+    (the common case: one process per GPU); the reference has no guard at all."""
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def __enter__(self):
+        idx = self.dev.index
+        self.prev = torch.cuda.current_device()
+        if idx is not None and idx != self.prev:
+            torch.cuda.set_device(idx)
+        else:
+            self.prev = None
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+_fn_cache = {}
+
+
+def _fn(name):
+    f = _fn_cache.get(name)
+    if f is None:
+        f = _fn_cache[name] = getattr(_native.load(), name)
+    return f
+
+
 def _workspace(lib, value, flags):
     B, S, H, D = value.shape
     n = lib.bxr_attn_bwd_workspace_bytes(value.element_size(), B, S, H, D, flags)
@@ -141,8 +173,8 @@ def box_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, att
     _step_check(B, im2col_step)
     lib = _native.load()
     out = torch.empty((B, Nq, H * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
-        st = getattr(lib, f"bxr_box_attn_fwd_{suf}")(
+    with _on_device(value.device):
+        st = _fn(f"bxr_box_attn_fwd_{suf}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), B, S, H, D, L, Nq, P,
             out.data_ptr(), _PATH_FLAGS, _stream(value.device))
@@ -162,9 +194,9 @@ def box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, at
     grad_value = torch.empty_like(value)
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         ws, ws_bytes = _workspace(lib, value, flags)
-        st = getattr(lib, f"bxr_box_attn_bwd_{suf}")(
+        st = _fn(f"bxr_box_attn_bwd_{suf}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
             B, S, H, D, L, Nq, P,
@@ -184,8 +216,8 @@ def instance_attn_forward(value, spatial_shapes, level_start_index, sampling_loc
     lib = _native.load()
     out = torch.empty((B, Nq, H * D), dtype=value.dtype, device=value.device)
     mask_out = torch.empty((B, Nq, P, H * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
-        st = getattr(lib, f"bxr_instance_attn_fwd_{suf}")(
+    with _on_device(value.device):
+        st = _fn(f"bxr_instance_attn_fwd_{suf}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), spatial_attn_weight.data_ptr(), level_attn_weight.data_ptr(),
             B, S, H, D, L, Nq, P, out.data_ptr(), mask_out.data_ptr(), _PATH_FLAGS, _stream(value.device))
@@ -211,9 +243,9 @@ def instance_attn_backward(value, spatial_shapes, level_start_index, sampling_lo
     grad_loc = torch.empty_like(sampling_loc)
     grad_sw = torch.empty_like(spatial_attn_weight)
     grad_lw = torch.empty_like(level_attn_weight)
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         ws, ws_bytes = _workspace(lib, value, flags)
-        st = getattr(lib, f"bxr_instance_attn_bwd_{suf}")(
+        st = _fn(f"bxr_instance_attn_bwd_{suf}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), spatial_attn_weight.data_ptr(), level_attn_weight.data_ptr(),
             grad_output.data_ptr(), grad_mask_output.data_ptr(),

@@ -1,0 +1,11 @@
+#!/bin/bash
+# compute-sanitizer over the small-shape GPU tests (memcheck + racecheck); logs under gpurun_out/<tag>/
+TAG=${1:-san}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+SEL='test_window_kernels_vs_oracle or test_instance_mask_head_vs_oracle or test_box_decoder_like_vs_oracle or test_misaligned or test_all_out_of_range or test_empty or test_six_d'
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py -q -x -k "$SEL" -p no:cacheprovider > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck.log
+tail -4 $OUT/memcheck.log
+SEL2='test_window_kernels_vs_oracle and (enc_box_K4 or enc_box_K2 or enc_uniform_K4) and f32'
+timeout 1500 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_ops.py -q -x -k "$SEL2" -p no:cacheprovider > $OUT/racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/racecheck.log
+grep -E "RACECHECK SUMMARY|hazard|passed|failed" $OUT/racecheck.log | sort | uniq -c | head -20
