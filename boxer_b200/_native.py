@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(_PKG, "_C")
 LIB_PATH = os.environ.get("BOXER_B200_LIB") or os.path.join(LIB_DIR, "libboxattn_b200.so")
 HEADER = os.path.join(ROOT, "include", "boxattn_b200.h")
 SOURCES = [os.path.join(CSRC, "boxattn_abi.cu")]
-DEPENDS = SOURCES + [os.path.join(CSRC, "boxattn_kernels.cuh"), os.path.join(CSRC, "boxattn_window.cuh"), os.path.join(CSRC, "boxattn_instance.cuh"), HEADER]
+DEPENDS = SOURCES + [os.path.join(CSRC, "boxattn_kernels.cuh"), os.path.join(CSRC, "boxattn_fused.cuh"), os.path.join(CSRC, "boxattn_window.cuh"), os.path.join(CSRC, "boxattn_instance.cuh"), HEADER]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -32,10 +32,11 @@ NVCC_FLAGS = [
 
 DTYPES = ("f32", "f64", "bf16")
 OPS = ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd")
+FUSED_OPS = ("box_grid_attn_fwd", "box_grid_attn_bwd")
 EXPORTS = (
     ["bxr_abi_version", "bxr_status_string", "bxr_last_error_detail", "bxr_last_launch_count",
-     "bxr_attn_bwd_workspace_bytes"]
-    + [f"bxr_{op}_{dt}" for op in OPS for dt in DTYPES]
+     "bxr_attn_bwd_workspace_bytes", "bxr_box_grid_attn_workspace_bytes"]
+    + [f"bxr_{op}_{dt}" for op in OPS + FUSED_OPS for dt in DTYPES]
 )
 
 _lock = threading.Lock()
@@ -96,6 +97,12 @@ def _declare(lib):
         f.restype, f.argtypes = i, [vp] * 6 + dims + [vp, vp, u, vp]
         f = getattr(lib, f"bxr_instance_attn_bwd_{dt}")
         f.restype, f.argtypes = i, [vp] * 8 + dims + [vp] * 4 + [vp, sz, u, vp]
+        f = getattr(lib, f"bxr_box_grid_attn_fwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 8 + dims + [vp] + [vp, sz, u, vp]
+        f = getattr(lib, f"bxr_box_grid_attn_bwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 9 + dims + [vp] * 4 + [vp, sz, u, vp]
+    lib.bxr_box_grid_attn_workspace_bytes.restype = c.c_size_t
+    lib.bxr_box_grid_attn_workspace_bytes.argtypes = [c.c_int] * 9 + [c.c_uint]
     return lib
 
 

@@ -28,10 +28,20 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .box_attention_func import (BoxAttnBf16Function, BoxAttnFunction, InstanceAttnBf16Function,
-                                 InstanceAttnFunction)
+from .box_attention_func import (BoxAttnBf16Function, BoxAttnFunction, BoxGridAttnBf16Function, BoxGridAttnFunction,
+                                 InstanceAttnBf16Function, InstanceAttnFunction)
 
 _AMP_NATIVE = False
+_FUSED_GRID = False
+
+
+def set_fused_grid(flag: bool):
+    """Opt in to the fused box -> grid -> attention op for ``BoxAttention`` / ``Box3dAttention`` (and
+    ``InstanceAttention`` when ``inferencing``): the modules hand the boxes (+ angles) to the op instead of the
+    materialised (B,Nq,H,L,P,2) sampling grid of ``_where_to_attend``.  Same outputs and gradients
+    (tests/test_gpu_fused.py); off by default so that the default path is the reference's, op for op."""
+    global _FUSED_GRID
+    _FUSED_GRID = bool(flag)
 
 
 def set_amp_native(flag: bool):
@@ -48,6 +58,11 @@ def _use_bf16(value):
 def _box_attn(value, v_shape, v_start_index, grid, weights, im2col_step):
     fn = BoxAttnBf16Function if _use_bf16(value) else BoxAttnFunction
     return fn.apply(value, v_shape, v_start_index, grid, weights, im2col_step)
+
+
+def _box_grid_attn(value, v_shape, v_start_index, boxes, angles, valid_ratios, kernel_indices, weights, im2col_step):
+    fn = BoxGridAttnBf16Function if _use_bf16(value) else BoxGridAttnFunction
+    return fn.apply(value, v_shape, v_start_index, boxes, angles, valid_ratios, kernel_indices, weights, im2col_step)
 
 
 def _instance_attn(value, v_shape, v_start_index, grid, sw, lw, k, im2col_step):
@@ -120,6 +135,30 @@ class _BoxAttentionBase(nn.Module):
             grid = grid * v_valid_ratios
         return grid.contiguous()
 
+    # the boxes _where_to_attend turns into a grid (box_attention.py:199-207); angles: None (no rotation)
+    def _boxes_and_angles(self, query, ref_windows):
+        b, l = ref_windows.shape[:2]
+        offset_boxes = F.linear(query, self.linear_box_weight, self.linear_box_bias)
+        offset_boxes = offset_boxes.view(b, l, self.num_head, self.num_level, 4)
+        if ref_windows.dim() == 3:
+            ref_windows = ref_windows[:, :, None, None]
+        else:
+            ref_windows = ref_windows.unsqueeze(3)
+        boxes = ref_windows + offset_boxes / 8 * ref_windows[..., [2, 3, 2, 3]]
+        return boxes, None
+
+    def _attend(self, query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, weights):
+        """box attention of `value` at the K x K grids of the query boxes: fused op or grid + op."""
+        if _FUSED_GRID and value.is_cuda:
+            boxes, angles = self._boxes_and_angles(query, ref_windows)
+            vr = None
+            if v_valid_ratios is not None:
+                vr = v_valid_ratios.reshape(v_valid_ratios.shape[0], self.num_level, 2)
+            return _box_grid_attn(value, v_shape, v_start_index, boxes, angles, vr, self.kernel_indices, weights,
+                                  self.im2col_step)
+        sampled_grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
+        return _box_attn(value, v_shape, v_start_index, sampled_grid, weights, self.im2col_step)
+
     def _project_value(self, value, v_mask):
         b, l2 = value.shape[:2]
         value = self.value_proj(value)
@@ -140,8 +179,7 @@ class BoxAttention(_BoxAttentionBase):
         attn_weights = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
         attn_weights = F.softmax(attn_weights.view(b, l1, self.num_head, -1), dim=-1)
         attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
-        sampled_grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
-        output = _box_attn(value, v_shape, v_start_index, sampled_grid, attn_weights, self.im2col_step)
+        output = self._attend(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, attn_weights)
         output = self.out_proj(output)
         return output, attn_weights
 
@@ -166,9 +204,9 @@ class InstanceAttention(_BoxAttentionBase):
 
         spatial_attn_weights = F.softmax(attn_weights.view(b, l1, self.num_head, -1), dim=-1)
         spatial_attn_weights = spatial_attn_weights.view(b, l1, self.num_head, self.num_level, k, k)
-        sampled_grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
 
         if not self.inferencing:
+            sampled_grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
             level_attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, k, k)
             level_attn_weights = F.softmax(level_attn_weights, dim=3)
             output, mask_output = _instance_attn(value, v_shape, v_start_index, sampled_grid,
@@ -176,7 +214,7 @@ class InstanceAttention(_BoxAttentionBase):
             attn_weights = (spatial_attn_weights, level_attn_weights)
             mask_output = self.out_proj(mask_output)
         else:
-            output = _box_attn(value, v_shape, v_start_index, sampled_grid, spatial_attn_weights, self.im2col_step)
+            output = self._attend(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, spatial_attn_weights)
             attn_weights = (spatial_attn_weights,)
             mask_output = None
         output = self.out_proj(output)
@@ -221,13 +259,30 @@ class Box3dAttention(_BoxAttentionBase):
             grid = grid * v_valid_ratios
         return grid.contiguous()
 
+    def _boxes_and_angles(self, query, ref_windows):
+        b, l = ref_windows.shape[:2]
+        offset_boxes = F.linear(query, self.linear_box_weight, self.linear_box_bias)
+        offset_boxes = offset_boxes.view(b, l, self.num_head, self.num_level, self.num_variable)
+        if ref_windows.dim() == 3:
+            ref_windows = ref_windows[:, :, None, None]
+            ref_windows, ref_angles, _ = ref_windows.split((4, 1, 2), dim=-1)
+        else:
+            ref_windows = ref_windows.unsqueeze(3)
+            ref_windows, ref_angles = ref_windows.split((4, 1), dim=-1)
+        if self.with_rotation:
+            offset_boxes, offset_angles = offset_boxes.split(4, dim=-1)
+            angles = (ref_angles + offset_angles / 16) * 2 * math.pi
+        else:
+            angles = ref_angles.expand(b, l, self.num_head, self.num_level, 1)
+        boxes = ref_windows + offset_boxes / 8 * ref_windows[..., [2, 3, 2, 3]]
+        return boxes, angles
+
     def forward(self, query, value, v_shape, v_mask, v_start_index, v_valid_ratios, ref_windows):
         b, l1 = query.shape[:2]
         value = self._project_value(value, v_mask)
         attn_weights = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
         attn_weights = F.softmax(attn_weights.view(b, l1, self.num_head, -1), dim=-1)
         attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
-        sampled_grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
-        output = _box_attn(value, v_shape, v_start_index, sampled_grid, attn_weights, self.im2col_step)
+        output = self._attend(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, attn_weights)
         output = self.out_proj(output)
         return output, attn_weights

@@ -74,6 +74,46 @@ class InstanceAttnFunction(Function):
         return grad_value, None, None, grad_loc, grad_sw, grad_lw, None, None
 
 
+class BoxGridAttnFunction(Function):
+    """Fused box -> K x K grid -> box attention (beyond the reference's surface).
+
+    ``apply(value, shapes, level_start_index, boxes, angles, valid_ratios, kernel_indices, attention_weights,
+    im2col_step)`` equals ``BoxAttnFunction.apply(value, shapes, lsi, grid, attention_weights, im2col_step)`` with
+    ``grid = (centre + R(angles) (kernel_indices * relu(size))) * valid_ratios`` as built by
+    ``BoxAttention._where_to_attend`` (box_attention.py:196-214) / ``Box3dAttention`` (:304-338), but the
+    (B,Nq,H,L,P,2) grid and its gradient are never materialised; gradients flow to ``boxes`` (B,Nq,H,L,4) and
+    ``angles`` (B,Nq,H,L[,1]).  ``valid_ratios`` (B,L,2 or the reference's B,1,1,L,1,2) and ``kernel_indices`` are
+    treated as constants, as they are in BoxeR."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, shapes, lsi, boxes, angles, valid_ratios, kernel_indices, attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.has = (angles is not None, valid_ratios is not None)
+        boxes = boxes.contiguous()
+        angles_c = angles.contiguous() if angles is not None else None
+        vr = valid_ratios.contiguous() if valid_ratios is not None else None
+        kidx = kernel_indices.to(boxes.dtype).contiguous()
+        out = ops.box_grid_attn_forward(value, shapes, lsi, boxes, angles_c, vr, kidx, attention_weights, im2col_step)
+        saved = [value, shapes, lsi, boxes, kidx, attention_weights] + [t for t in (angles_c, vr) if t is not None]
+        ctx.save_for_backward(*saved)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_contiguous():
+            grad_output = grad_output.contiguous()
+        value, shapes, lsi, boxes, kidx, attn = ctx.saved_tensors[:6]
+        rest = list(ctx.saved_tensors[6:])
+        angles = rest.pop(0) if ctx.has[0] else None
+        vr = rest.pop(0) if ctx.has[1] else None
+        gv, gb, ga, gw = ops.box_grid_attn_backward(value, shapes, lsi, boxes, angles, vr, kidx, attn,
+                                                    grad_output.to(value.dtype), ctx.im2col_step)
+        return gv, None, None, gb, ga, None, None, gw, None
+
+
 # --------------------------------------------------------------------------- bf16 opt-in
 def _bf16_inputs(value, loc, *weights):
     return (value.to(torch.bfloat16).contiguous(), loc.float().contiguous(),
@@ -127,3 +167,36 @@ class InstanceAttnBf16Function(Function):
                 grad_mask_output.to(torch.bfloat16).contiguous(), ctx.im2col_step)
         dv, dl, ds, dw = ctx.in_dtypes
         return gv.to(dv), None, None, gl.to(dl), gs.to(ds), gw.to(dw), None, None
+
+
+class BoxGridAttnBf16Function(Function):
+    """bf16 value / output variant of BoxGridAttnFunction (boxes, angles, weights fp32)."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, lsi, boxes, angles, valid_ratios, kernel_indices, attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.has = (angles is not None, valid_ratios is not None)
+        ctx.in_dtypes = (value.dtype, boxes.dtype, angles.dtype if angles is not None else None, attention_weights.dtype)
+        with torch.autocast("cuda", enabled=False):
+            v = value.to(torch.bfloat16).contiguous()
+            bx = boxes.float().contiguous()
+            an = angles.float().contiguous() if angles is not None else None
+            vr = valid_ratios.float().contiguous() if valid_ratios is not None else None
+            kidx = kernel_indices.float().contiguous()
+            a = attention_weights.float().contiguous()
+            out = ops.box_grid_attn_forward(v, shapes, lsi, bx, an, vr, kidx, a, im2col_step)
+        ctx.save_for_backward(*([v, shapes, lsi, bx, kidx, a] + [t for t in (an, vr) if t is not None]))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        v, shapes, lsi, bx, kidx, a = ctx.saved_tensors[:6]
+        rest = list(ctx.saved_tensors[6:])
+        an = rest.pop(0) if ctx.has[0] else None
+        vr = rest.pop(0) if ctx.has[1] else None
+        with torch.autocast("cuda", enabled=False):
+            gv, gb, ga, gw = ops.box_grid_attn_backward(v, shapes, lsi, bx, an, vr, kidx, a,
+                                                        grad_output.to(torch.bfloat16).contiguous(), ctx.im2col_step)
+        dv, db, da, dw = ctx.in_dtypes
+        return (gv.to(dv), None, None, gb.to(db), ga.to(da) if ga is not None else None, None, None, gw.to(dw), None)

@@ -11,6 +11,7 @@
 #include "boxattn_kernels.cuh"
 #include "boxattn_window.cuh"
 #include "boxattn_instance.cuh"
+#include "boxattn_fused.cuh"
 #include "../../include/boxattn_b200.h"
 
 namespace {
@@ -170,15 +171,15 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
     return p.rows >= 2LL * sm_count() * groups;     // small (decoder-sized) calls keep the point-split kernels
 }
 
-template <typename TV, int G, int SUB, int PPL>
+template <typename TV, int G, int SUB, int PPL, bool FUSED>
 int fwd_win(AttnParams& p, cudaStream_t st) {
     p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL>>(p, st, "box_fwd_win_kernel");
+    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED>>(p, st, "box_fwd_win_kernel");
 }
-template <typename TV, int G, int SUB, int PPL, typename ACC>
+template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED>
 int bwd_win(AttnParams& p, cudaStream_t st) {
     p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC>>(p, st, "box_bwd_win_kernel");
+    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED>>(p, st, "box_bwd_win_kernel");
 }
 
 // (G, SUB, PPL): SUB lanes share a level's points, PPL points per lane; P <= SUB * PPL.
@@ -203,13 +204,26 @@ int win_key(int P, int g) {
     return g * 1000 + sub * 10 + ppl;
 }
 
-template <typename TV>
+template <typename TV, bool FUSED = false>
 int dispatch_fwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_win<TV, G, SUB, PPL>(p, st)))
+    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_win<TV, G, SUB, PPL, FUSED>(p, st)))
 }
-template <typename TV, typename ACC>
+template <typename TV, typename ACC, bool FUSED = false>
 int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC>(p, st)))
+    BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC, FUSED>(p, st)))
+}
+
+// the fused (box -> grid) window kernels apply whenever the vector layout does; no row-count threshold
+bool fused_applies(int dtype_bytes, int B, int S, int H, int D, int L, int P, unsigned flags) {
+    if (flags & BXR_FLAG_PATH_POINT) return false;
+    if (dtype_bytes != 4 && dtype_bytes != 2) return false;
+    const int vec = 16 / dtype_bytes;
+    if (D <= 0 || D % vec) return false;
+    const int g = D / vec;
+    if (g != 4 && g != 8 && g != 16) return false;
+    if (P < 1 || P > 4 * g || (long long)L * P >= 65536) return false;
+    if ((long long)B * S * g * H >= 0xffffffffLL) return false;
+    return true;
 }
 
 // ---- owner-tap instance kernels (boxattn_instance.cuh)
@@ -323,11 +337,22 @@ int finalize(const ACC* acc, TV* out, long long n, const float* scale, cudaStrea
     return BXR_OK;
 }
 
+// fused box->grid inputs handed through backward()/forward() (null for the location-taking ops)
+struct FusedArgs {
+    const void* boxes = nullptr;
+    const void* angles = nullptr;
+    const void* valid_ratios = nullptr;
+    const void* kidx = nullptr;
+    void* grad_boxes = nullptr;
+    void* grad_angles = nullptr;
+};
+
 template <typename TV, typename TW, bool INSTANCE>
 int backward(const TV* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, const TW* w0, const TW* w1,
              const TV* grad_out, const TV* grad_mask, int B, int S, int H, int D, int L, int Nq, int P,
              TV* grad_value, TW* grad_loc, TW* grad_w0, TW* grad_w1,
-             void* workspace, size_t workspace_bytes_given, unsigned flags, bxr_stream_t stream) {
+             void* workspace, size_t workspace_bytes_given, unsigned flags, bxr_stream_t stream,
+             const FusedArgs* fused = nullptr) {
     using TC = typename Compute<TV>::type;
     g_launches = 0;
     g_detail[0] = 0;
@@ -343,14 +368,18 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
         BXR_CUDA(cudaMemsetAsync(grad_value, 0, sizeof(TV) * (size_t)n_value, st));
     }
     if (p.rows == 0 || p.LP == 0) return BXR_OK;
-    if (!grad_loc || !grad_w0 || (INSTANCE && !grad_w1)) return fail(BXR_ERR_NULL_POINTER, "gradient pointer is NULL");
+    if ((!fused && !grad_loc) || !grad_w0 || (INSTANCE && !grad_w1)) return fail(BXR_ERR_NULL_POINTER, "gradient pointer is NULL");
     if (D == 0 || S == 0) {   // no channels / no pixels: all gradients are zero
+        if (fused) {
+            BXR_CUDA(cudaMemsetAsync(fused->grad_boxes, 0, sizeof(TW) * (size_t)p.rows * p.L * 4, st));
+            if (fused->grad_angles) BXR_CUDA(cudaMemsetAsync(fused->grad_angles, 0, sizeof(TW) * (size_t)p.rows * p.L, st));
+        } else
         BXR_CUDA(cudaMemsetAsync(grad_loc, 0, sizeof(TW) * (size_t)p.rows * p.LP * 2, st));
         BXR_CUDA(cudaMemsetAsync(grad_w0, 0, sizeof(TW) * (size_t)p.rows * p.LP, st));
         if (INSTANCE) BXR_CUDA(cudaMemsetAsync(grad_w1, 0, sizeof(TW) * (size_t)p.rows * p.LP, st));
         return BXR_OK;
     }
-    if (!value || !shapes || !level_start || !loc || !w0 || !grad_out || (INSTANCE && (!w1 || !grad_mask)))
+    if (!value || !shapes || !level_start || (!fused && !loc) || !w0 || !grad_out || (INSTANCE && (!w1 || !grad_mask)))
         return fail(BXR_ERR_NULL_POINTER, "input pointer is NULL");
 
     const size_t need = workspace_bytes((int)sizeof(TV), n_value, flags);
@@ -360,6 +389,10 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
     p.value = value; p.shapes = shapes; p.level_start = level_start;
     p.loc = loc; p.w0 = w0; p.w1 = w1; p.grad_out = grad_out; p.grad_mask = grad_mask;
     p.grad_loc = grad_loc; p.grad_w0 = grad_w0; p.grad_w1 = grad_w1;
+    if (fused) {
+        p.boxes = fused->boxes; p.angles = fused->angles; p.valid_ratios = fused->valid_ratios; p.kidx = fused->kidx;
+        p.grad_boxes = fused->grad_boxes; p.grad_angles = fused->grad_angles;
+    }
 
     unsigned* bits = nullptr;
     float* scale = nullptr;
@@ -388,15 +421,20 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
     int status;
     const int g = vec_group<TV>(D, p.LP);
     const bool vec_ok = g && aligned16(value) && aligned16(grad_out) && aligned16(acc) && (!INSTANCE || aligned16(grad_mask)) &&
-                        aligned8(loc) && aligned8(grad_loc);
+                        (fused ? (aligned16(fused->boxes) && aligned16(fused->grad_boxes) && aligned8(fused->kidx) &&
+                                  (!fused->valid_ratios || aligned8(fused->valid_ratios)))
+                               : (aligned8(loc) && aligned8(grad_loc)));
+    if (fused && !vec_ok) return fail(BXR_ERR_UNSUPPORTED, "fused backward reached with a layout the fused kernels do not cover");
     if constexpr (!std::is_same<TV, double>::value) {
         bool win = false;
-        if constexpr (!INSTANCE) win = vec_ok && use_window(p, g, flags);
+        if constexpr (!INSTANCE) win = vec_ok && (fused ? true : use_window(p, g, flags));
         bool own = false;
         if constexpr (INSTANCE) own = vec_ok && use_inst_own(p, g, flags);
         if (win) {
-            if constexpr (!INSTANCE)
-                status = det ? dispatch_bwd_win<TV, long long>(g, p, st) : dispatch_bwd_win<TV, float>(g, p, st);
+            if constexpr (!INSTANCE) {
+                if (fused) status = det ? dispatch_bwd_win<TV, long long, true>(g, p, st) : dispatch_bwd_win<TV, float, true>(g, p, st);
+                else status = det ? dispatch_bwd_win<TV, long long>(g, p, st) : dispatch_bwd_win<TV, float>(g, p, st);
+            }
         } else if (own) {
             if constexpr (INSTANCE) {
                 if (g == 8) status = det ? bwd_inst_own<TV, 8, long long>(p, st) : bwd_inst_own<TV, 8, float>(p, st);
@@ -416,6 +454,144 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
 
     if (det) return finalize<TV, long long>(static_cast<const long long*>(acc), grad_value, n_value, scale, st);
     if (sizeof(TV) == 2) return finalize<TV, float>(static_cast<const float*>(acc), grad_value, n_value, nullptr, st);
+    return BXR_OK;
+}
+
+// -------------------------------------------------------------------------------- fused box -> grid
+size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+template <typename TW>
+int launch_grid_gen(const AttnParams& p, TW* loc, cudaStream_t st) {
+    const long long n = p.rows * p.LP;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    grid_gen_kernel<TW><<<(int)blocks, 256, 0, st>>>(p, loc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "grid_gen_kernel");
+    ++g_launches;
+    return BXR_OK;
+}
+
+template <typename TW>
+int launch_grid_bwd(const AttnParams& p, const TW* grad_loc, cudaStream_t st) {
+    const long long n = p.rows * p.L;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    grid_bwd_kernel<TW><<<(int)blocks, 256, 0, st>>>(p, grad_loc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "grid_bwd_kernel");
+    ++g_launches;
+    return BXR_OK;
+}
+
+size_t fused_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H, int D, int L, int Nq, int P, unsigned flags) {
+    if (B < 0 || S < 0 || H < 0 || D < 0 || L < 0 || Nq < 0 || P < 0) return 0;
+    const size_t tw = dtype_bytes == 8 ? 8 : 4;
+    const size_t loc_bytes = align256((size_t)B * Nq * H * L * P * 2 * tw);
+    const bool fused = fused_applies(dtype_bytes, B, S, H, D, L, P, flags);
+    size_t n = 0;
+    if (backward) n += align256(workspace_bytes(dtype_bytes, (long long)B * S * H * D, flags));
+    if (!fused) n += loc_bytes * (backward ? 2 : 1);
+    return n;
+}
+
+template <typename TV, typename TW>
+int fused_forward(const TV* value, const int64_t* shapes, const int64_t* level_start, const TW* boxes, const TW* angles,
+                  const TW* valid_ratios, const TW* kidx, const TW* attn, int B, int S, int H, int D, int L, int Nq, int P,
+                  TV* out, void* ws, size_t ws_bytes, unsigned flags, bxr_stream_t stream) {
+    g_launches = 0;
+    g_detail[0] = 0;
+    if (int s = check_dims(B, S, H, D, L, Nq, P)) return s;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    fill_sizes(p, B, S, H, D, L, Nq, P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p.rows == 0 || D == 0) return BXR_OK;
+    if (!out) return fail(BXR_ERR_NULL_POINTER, "output pointer is NULL");
+    if (p.LP == 0 || S == 0) {
+        BXR_CUDA(cudaMemsetAsync(out, 0, sizeof(TV) * (size_t)p.rows * D, st));
+        return BXR_OK;
+    }
+    if (!value || !shapes || !level_start || !boxes || !kidx || !attn) return fail(BXR_ERR_NULL_POINTER, "input pointer is NULL");
+    p.value = value; p.shapes = shapes; p.level_start = level_start; p.w0 = attn; p.out = out;
+    p.boxes = boxes; p.angles = angles; p.valid_ratios = valid_ratios; p.kidx = kidx;
+
+    const bool aligned = aligned16(value) && aligned16(out) && aligned16(boxes) && aligned8(kidx) && (!valid_ratios || aligned8(valid_ratios));
+    if constexpr (!std::is_same<TV, double>::value) {
+        if (aligned && fused_applies((int)sizeof(TV), B, S, H, D, L, P, flags)) {
+            const int g = vec_group<TV>(D, p.LP);
+            return dispatch_fwd_win<TV, true>(g, p, st);
+        }
+    }
+    // general path: materialise the grid, then the location-taking op
+    const size_t loc_bytes = align256((size_t)p.rows * p.LP * 2 * sizeof(TW));
+    if (!ws || ws_bytes < loc_bytes || !aligned16(ws)) return fail(BXR_ERR_WORKSPACE, "workspace too small for the sampling grid");
+    TW* loc = static_cast<TW*>(ws);
+    if (int s = launch_grid_gen<TW>(p, loc, st)) return s;
+    const int n0 = g_launches;
+    const int status = forward<TV, TW, false>(value, shapes, level_start, loc, attn, nullptr, B, S, H, D, L, Nq, P, out, nullptr,
+                                              flags, stream);
+    g_launches += n0;
+    return status;
+}
+
+template <typename TV, typename TW>
+int fused_backward(const TV* value, const int64_t* shapes, const int64_t* level_start, const TW* boxes, const TW* angles,
+                   const TW* valid_ratios, const TW* kidx, const TW* attn, const TV* grad_out,
+                   int B, int S, int H, int D, int L, int Nq, int P, TV* grad_value, TW* grad_boxes, TW* grad_angles,
+                   TW* grad_attn, void* ws, size_t ws_bytes, unsigned flags, bxr_stream_t stream) {
+    g_detail[0] = 0;
+    if (int s = check_dims(B, S, H, D, L, Nq, P)) return s;
+    const long long rows = (long long)B * Nq * H;
+    if (rows > 0 && L > 0 && (!boxes || !kidx || !grad_boxes || (angles && !grad_angles)))
+        return fail(BXR_ERR_NULL_POINTER, "box pointer is NULL");
+    FusedArgs fa;
+    fa.boxes = boxes; fa.angles = angles; fa.valid_ratios = valid_ratios; fa.kidx = kidx;
+    fa.grad_boxes = grad_boxes; fa.grad_angles = angles ? grad_angles : nullptr;
+    const size_t bwd_ws = align256(workspace_bytes((int)sizeof(TV), (long long)B * S * H * D, flags));
+    if (bwd_ws && (!ws || ws_bytes < bwd_ws)) return fail(BXR_ERR_WORKSPACE, "workspace too small");
+
+    bool fused = false;
+    if constexpr (!std::is_same<TV, double>::value) {
+        fused = fused_applies((int)sizeof(TV), B, S, H, D, L, P, flags) && aligned16(value) && aligned16(grad_out) &&
+                aligned16(grad_value) && aligned16(boxes) && aligned16(grad_boxes) && aligned8(kidx) &&
+                (!valid_ratios || aligned8(valid_ratios)) && (!ws || aligned16(ws));
+    }
+    if (fused)
+        return backward<TV, TW, false>(value, shapes, level_start, nullptr, attn, nullptr, grad_out, nullptr, B, S, H, D, L, Nq, P,
+                                       grad_value, nullptr, grad_attn, nullptr, ws, ws_bytes, flags, stream, &fa);
+
+    // general path: grid -> location-taking backward -> chain to the boxes
+    const size_t loc_bytes = align256((size_t)rows * L * P * 2 * sizeof(TW));
+    if (rows > 0 && (long long)L * P > 0) {
+        if (!ws || ws_bytes < bwd_ws + 2 * loc_bytes || !aligned16(ws)) return fail(BXR_ERR_WORKSPACE, "workspace too small for the sampling grid");
+    }
+    TW* loc = reinterpret_cast<TW*>(static_cast<char*>(ws) + bwd_ws);
+    TW* gloc = reinterpret_cast<TW*>(static_cast<char*>(ws) + bwd_ws + loc_bytes);
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    fill_sizes(p, B, S, H, D, L, Nq, P);
+    p.boxes = boxes; p.angles = angles; p.valid_ratios = valid_ratios; p.kidx = kidx;
+    p.grad_boxes = grad_boxes; p.grad_angles = fa.grad_angles;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int extra = 0;
+    if (p.rows > 0 && p.LP > 0) {
+        g_launches = 0;
+        if (int s = launch_grid_gen<TW>(p, loc, st)) return s;
+        extra = g_launches;
+    }
+    int status = backward<TV, TW, false>(value, shapes, level_start, loc, attn, nullptr, grad_out, nullptr, B, S, H, D, L, Nq, P,
+                                         grad_value, gloc, grad_attn, nullptr, ws, bwd_ws, flags, stream);
+    if (status) return status;
+    extra += g_launches;
+    if (p.rows > 0 && p.LP > 0) {
+        if (int s = launch_grid_bwd<TW>(p, gloc, st)) return s;
+        extra += 1;
+    } else if (p.rows > 0 && p.L > 0) {
+        BXR_CUDA(cudaMemsetAsync(grad_boxes, 0, sizeof(TW) * (size_t)p.rows * p.L * 4, st));
+        if (fa.grad_angles) BXR_CUDA(cudaMemsetAsync(fa.grad_angles, 0, sizeof(TW) * (size_t)p.rows * p.L, st));
+    }
+    g_launches = extra;
     return BXR_OK;
 }
 
@@ -484,5 +660,35 @@ size_t bxr_attn_bwd_workspace_bytes(int dtype_bytes, int B, int S, int H, int D,
 BXR_DEFINE_OPS(f32, float, float, float)
 BXR_DEFINE_OPS(f64, double, double, double)
 BXR_DEFINE_OPS(bf16, bxr_bf16, __nv_bfloat16, float)
+
+size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H, int D, int L, int Nq, int P,
+                                         unsigned flags) {
+    return fused_workspace_bytes(dtype_bytes, backward, B, S, H, D, L, Nq, P, flags);
+}
+
+#define BXR_DEFINE_FUSED(SUF, TVABI, TV, TW)                                                                         \
+    int bxr_box_grid_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
+                                    const TW* boxes, const TW* angles, const TW* valid_ratios, const TW* kidx,       \
+                                    const TW* attn, int B, int S, int H, int D, int L, int Nq, int P, TVABI* out,    \
+                                    void* workspace, size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {  \
+        return fused_forward<TV, TW>(reinterpret_cast<const TV*>(value), shapes, level_start, boxes, angles,         \
+                                     valid_ratios, kidx, attn, B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out),     \
+                                     workspace, workspace_bytes, flags, stream);                                     \
+    }                                                                                                                \
+    int bxr_box_grid_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
+                                    const TW* boxes, const TW* angles, const TW* valid_ratios, const TW* kidx,       \
+                                    const TW* attn, const TVABI* grad_out, int B, int S, int H, int D, int L,        \
+                                    int Nq, int P, TVABI* grad_value, TW* grad_boxes, TW* grad_angles,               \
+                                    TW* grad_attn, void* workspace, size_t workspace_bytes, unsigned flags,          \
+                                    bxr_stream_t stream) {                                                           \
+        return fused_backward<TV, TW>(reinterpret_cast<const TV*>(value), shapes, level_start, boxes, angles,        \
+                                      valid_ratios, kidx, attn, reinterpret_cast<const TV*>(grad_out), B, S, H, D,   \
+                                      L, Nq, P, reinterpret_cast<TV*>(grad_value), grad_boxes, grad_angles,          \
+                                      grad_attn, workspace, workspace_bytes, flags, stream);                         \
+    }
+
+BXR_DEFINE_FUSED(f32, float, float, float)
+BXR_DEFINE_FUSED(f64, double, double, double)
+BXR_DEFINE_FUSED(bf16, bxr_bf16, __nv_bfloat16, float)
 
 }  // extern "C"

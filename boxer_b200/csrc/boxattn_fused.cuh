@@ -1,0 +1,82 @@
+// Fused "box -> K x K grid -> attention" entry points.
+//
+// The reference builds the sampling grid in PyTorch (BoxAttention._where_to_attend,
+// box_attention.py:196-214; Box3dAttention adds the rotation, :304-338), materialising a
+// (B, Nq, H, L, P, 2) tensor that the op then re-reads, and autograd materialises its gradient.
+// Here the op takes the boxes themselves:
+//     loc[b,q,h,l,p] = (centre + R(angle) (kernel_index_p * relu(size))) * valid_ratio[b,l]
+// The footprint-window kernels generate the points in registers (boxattn_window.cuh, FUSED) and
+// reduce the per-point location gradients to the 4 (+1) box gradients in-kernel.  Shapes those
+// kernels do not cover (odd head dims, fp64, tiny calls, huge grids) go through the two small
+// kernels below around the location-taking op -- same interface, same results.
+#pragma once
+
+#include "boxattn_kernels.cuh"
+
+namespace bxr {
+
+template <typename TW>
+__global__ void grid_gen_kernel(const AttnParams p, TW* __restrict__ loc_out) {
+    const TW* __restrict__ boxes = static_cast<const TW*>(p.boxes);
+    const TW* __restrict__ angles = static_cast<const TW*>(p.angles);
+    const TW* __restrict__ vr = static_cast<const TW*>(p.valid_ratios);
+    const TW* __restrict__ kidx = static_cast<const TW*>(p.kidx);
+    const long long n = p.rows * p.LP;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (long long)gridDim.x * blockDim.x) {
+        const int pt = (int)(s % p.P);
+        const long long rl = s / p.P;
+        const int l = (int)(rl % p.L);
+        const long long b = rl / ((long long)p.L * p.H * p.Nq);
+        const TW cx = boxes[rl * 4], cy = boxes[rl * 4 + 1];
+        const TW sx = boxes[rl * 4 + 2] > (TW)0 ? boxes[rl * 4 + 2] : (TW)0;
+        const TW sy = boxes[rl * 4 + 3] > (TW)0 ? boxes[rl * 4 + 3] : (TW)0;
+        const TW ux = kidx[2 * pt] * sx, uy = kidx[2 * pt + 1] * sy;
+        TW cs = 1, sn = 0;
+        if (angles) { cs = cos(angles[rl]); sn = sin(angles[rl]); }
+        TW x = cx + (ux * cs - uy * sn), y = cy + (ux * sn + uy * cs);
+        if (vr) { x *= vr[(b * p.L + l) * 2]; y *= vr[(b * p.L + l) * 2 + 1]; }
+        loc_out[2 * s] = x;
+        loc_out[2 * s + 1] = y;
+    }
+}
+
+// one thread per (row, level): reduce the P location gradients to the box / angle gradients
+template <typename TW>
+__global__ void grid_bwd_kernel(const AttnParams p, const TW* __restrict__ grad_loc) {
+    const TW* __restrict__ boxes = static_cast<const TW*>(p.boxes);
+    const TW* __restrict__ angles = static_cast<const TW*>(p.angles);
+    const TW* __restrict__ vr = static_cast<const TW*>(p.valid_ratios);
+    const TW* __restrict__ kidx = static_cast<const TW*>(p.kidx);
+    TW* __restrict__ gb = static_cast<TW*>(p.grad_boxes);
+    TW* __restrict__ ga = static_cast<TW*>(p.grad_angles);
+    const long long n = p.rows * p.L;
+    for (long long rl = (long long)blockIdx.x * blockDim.x + threadIdx.x; rl < n; rl += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(rl % p.L);
+        const long long b = rl / ((long long)p.L * p.H * p.Nq);
+        const bool pw = boxes[rl * 4 + 2] > (TW)0, ph = boxes[rl * 4 + 3] > (TW)0;
+        const TW sx = pw ? boxes[rl * 4 + 2] : (TW)0, sy = ph ? boxes[rl * 4 + 3] : (TW)0;
+        TW cs = 1, sn = 0;
+        if (angles) { cs = cos(angles[rl]); sn = sin(angles[rl]); }
+        TW vx = 1, vy = 1;
+        if (vr) { vx = vr[(b * p.L + l) * 2]; vy = vr[(b * p.L + l) * 2 + 1]; }
+        TW bcx = 0, bcy = 0, bw = 0, bh = 0, ba = 0;
+        for (int pt = 0; pt < p.P; ++pt) {
+            const long long s = rl * p.P + pt;
+            const TW gx = grad_loc[2 * s] * vx, gy = grad_loc[2 * s + 1] * vy;
+            const TW kx = kidx[2 * pt], ky = kidx[2 * pt + 1];
+            const TW ux = kx * sx, uy = ky * sy;
+            bcx += gx;
+            bcy += gy;
+            bw += kx * (gx * cs + gy * sn);
+            bh += ky * (gy * cs - gx * sn);
+            ba += gx * (-ux * sn - uy * cs) + gy * (ux * cs - uy * sn);
+        }
+        gb[rl * 4] = bcx;
+        gb[rl * 4 + 1] = bcy;
+        gb[rl * 4 + 2] = pw ? bw : (TW)0;
+        gb[rl * 4 + 3] = ph ? bh : (TW)0;
+        if (ga) ga[rl] = ba;
+    }
+}
+
+}  // namespace bxr

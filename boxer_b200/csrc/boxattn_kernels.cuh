@@ -50,6 +50,13 @@ struct AttnParams {
     void* grad_w0;                // TW
     void* grad_w1;                // TW
     const float* det_scale;       // device scalar: power-of-two scale of the fixed-point scatter (DET)
+    // fused box -> grid entry points (boxattn_fused.cuh): locations are generated in-kernel
+    const void* boxes;            // (B,Nq,H,L,4) TW  cx, cy, w, h (normalised)
+    const void* angles;           // (B,Nq,H,L)   TW  radians, or nullptr
+    const void* valid_ratios;     // (B,L,2)      TW  (x, y), or nullptr
+    const void* kidx;             // (P,2)        TW  kernel_indices
+    void* grad_boxes;             // (B,Nq,H,L,4) TW
+    void* grad_angles;            // (B,Nq,H,L)   TW  or nullptr
     // sizes
     int B, S, H, D, L, Nq, P;
     int LP;                       // L*P

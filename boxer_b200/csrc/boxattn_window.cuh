@@ -91,15 +91,11 @@ struct LanePoint {
     bool inside;      // window test of box_attn_kernel.cuh:328 (false for padding lanes)
 };
 
-__device__ __forceinline__ LanePoint lane_point(const float* __restrict__ loc_l, const float* __restrict__ w_l,
-                                                int pt, int P, int h, int w) {
+__device__ __forceinline__ LanePoint lane_point_xy(float lx_n, float ly_n, float aw, bool act, int h, int w) {
     LanePoint t;
-    const bool act = pt < P;
-    const int pc = act ? pt : 0;
-    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc_l) + pc);
-    t.aw = __ldg(w_l + pc);
-    const float x = xy.x * (float)w - 0.5f;
-    const float y = xy.y * (float)h - 0.5f;
+    t.aw = aw;
+    const float x = lx_n * (float)w - 0.5f;
+    const float y = ly_n * (float)h - 0.5f;
     t.inside = act && (y > -1.f) && (x > -1.f) && (y < (float)h) && (x < (float)w);
     const float xs = t.inside ? x : 0.f, ys = t.inside ? y : 0.f;
     const float xf = floorf(xs), yf = floorf(ys);
@@ -108,6 +104,59 @@ __device__ __forceinline__ LanePoint lane_point(const float* __restrict__ loc_l,
     t.lx = xs - xf;
     t.ly = ys - yf;
     return t;
+}
+
+__device__ __forceinline__ LanePoint lane_point(const float* __restrict__ loc_l, const float* __restrict__ w_l,
+                                                int pt, int P, int h, int w) {
+    const bool act = pt < P;
+    const int pc = act ? pt : 0;
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc_l) + pc);
+    return lane_point_xy(xy.x, xy.y, __ldg(w_l + pc), act, h, w);
+}
+
+// One (row, level) box of the fused entry points: the K x K grid of BoxAttention._where_to_attend
+// (box_attention.py:196-214) / Box3dAttention (:304-338) generated in registers:
+//   loc_p = (centre + R(angle) (kernel_index_p * relu(size))) * valid_ratio
+struct LevelBox {
+    float cx, cy, sx, sy;     // sx, sy = relu(w), relu(h)
+    float cs, sn;             // cos / sin of the angle (1, 0 without rotation)
+    float vx, vy;             // valid ratios (1, 1 without)
+    bool pos_w, pos_h;        // w > 0, h > 0 (relu gradient)
+};
+
+__device__ __forceinline__ LevelBox load_level_box(const AttnParams& p, long long rl, long long b, int l) {
+    LevelBox q;
+    const float4 bx = __ldg(reinterpret_cast<const float4*>(p.boxes) + rl);
+    q.cx = bx.x; q.cy = bx.y;
+    q.pos_w = bx.z > 0.f; q.pos_h = bx.w > 0.f;
+    q.sx = q.pos_w ? bx.z : 0.f; q.sy = q.pos_h ? bx.w : 0.f;
+    q.cs = 1.f; q.sn = 0.f;
+    if (p.angles) {
+        const float a = __ldg(static_cast<const float*>(p.angles) + rl);
+        sincosf(a, &q.sn, &q.cs);
+    }
+    q.vx = q.vy = 1.f;
+    if (p.valid_ratios) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p.valid_ratios) + (b * p.L + l));
+        q.vx = v.x; q.vy = v.y;
+    }
+    return q;
+}
+
+__device__ __forceinline__ void box_point(const LevelBox& q, float kx, float ky, float& x, float& y) {
+    const float ux = kx * q.sx, uy = ky * q.sy;
+    x = (q.cx + (ux * q.cs - uy * q.sn)) * q.vx;
+    y = (q.cy + (ux * q.sn + uy * q.cs)) * q.vy;
+}
+
+__device__ __forceinline__ LanePoint lane_point_box(const LevelBox& q, const float* __restrict__ kidx,
+                                                    const float* __restrict__ w_l, int pt, int P, int h, int w) {
+    const bool act = pt < P;
+    const int pc = act ? pt : 0;
+    const float2 k = __ldg(reinterpret_cast<const float2*>(kidx) + pc);
+    float x, y;
+    box_point(q, k.x, k.y, x, y);
+    return lane_point_xy(x, y, __ldg(w_l + pc), act, h, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -150,7 +199,7 @@ struct SubWin {
 
 // ------------------------------------------------------------------------------------------------
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
-template <typename TV, int G, int SUB, int PPL>
+template <typename TV, int G, int SUB, int PPL, bool FUSED>
 __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_FWD_MINB) box_fwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
@@ -181,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_FWD_MINB
         const long long b = row / ((long long)p.H * p.Nq);
         // value addressing in 16-byte units (one lane chunk) as 32-bit indices off the tensor base
         const unsigned vrow = (unsigned)(b * p.S * HDV + head * G + lane);
-        const float* loc_row = loc + row * p.LP * 2;
+        const float* loc_row = FUSED ? nullptr : loc + row * p.LP * 2;
         const float* w_row = w0 + row * p.LP;
 
         float acc[VEC];
@@ -197,9 +246,13 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_FWD_MINB
             LanePoint pt[PPL];
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
             float S = 0.f;
+            LevelBox lbx;
+            if constexpr (FUSED) lbx = load_level_box(p, row * p.L + lmc, b, lmc);
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
-                pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, lact ? slane + k * SUB : p.P, p.P, mh, mw);
+                const int ptn = lact ? slane + k * SUB : p.P;
+                if constexpr (FUSED) pt[k] = lane_point_box(lbx, static_cast<const float*>(p.kidx), w_row + lmc * p.P, ptn, p.P, mh, mw);
+                else pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, ptn, p.P, mh, mw);
                 if (pt[k].inside) {
                     bx0 = min(bx0, pt[k].x0); bx1 = max(bx1, pt[k].x0 + 1);
                     by0 = min(by0, pt[k].y0); by1 = max(by1, pt[k].y0 + 1);
@@ -367,7 +420,7 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
     return (hi ? 2 : 0) + (lo ? 1 : 0);
 }
 
-template <typename TV, int G, int SUB, int PPL, typename ACC>
+template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED>
 __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB) box_bwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
@@ -404,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB
         const int head = (int)(row % p.H);
         const long long b = row / ((long long)p.H * p.Nq);
         const unsigned vbase = (unsigned)(b * p.S * HDV + head * G + lane);
-        const float* loc_row = loc + row * p.LP * 2;
+        const float* loc_row = FUSED ? nullptr : loc + row * p.LP * 2;
         const float* w_row = w0 + row * p.LP;
         float go[VEC];
         V::load(static_cast<const TV*>(p.grad_out) + (row * p.D + lane * VEC), go);
@@ -418,9 +471,13 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB
             float g_a[PPL], g_x[PPL], g_y[PPL];     // this lane's results for its own points
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
             float S = 0.f;
+            LevelBox lbx;
+            if constexpr (FUSED) lbx = load_level_box(p, row * p.L + lmc, b, lmc);
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
-                pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, lact ? slane + k * SUB : p.P, p.P, mh, mw);
+                const int ptn = lact ? slane + k * SUB : p.P;
+                if constexpr (FUSED) pt[k] = lane_point_box(lbx, static_cast<const float*>(p.kidx), w_row + lmc * p.P, ptn, p.P, mh, mw);
+                else pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, ptn, p.P, mh, mw);
                 g_a[k] = g_x[k] = g_y[k] = 0.f;
                 if (pt[k].inside) {
                     bx0 = min(bx0, pt[k].x0); bx1 = max(bx1, pt[k].x0 + 1);
@@ -521,7 +578,8 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB
                             if (wi[j] != 0) scatter_row<ACC, VEC>(gacc + (size_t)offs[j] * VEC, go, (float)wi[j] * inv_scale, dscale);
                         }
                         float total;
-                        const int mine = reduce4<G>(dsum, total, lane, gm);   // also orders the flag reads before the writes
+                        const int mine = reduce4<G>(dsum, total, lane, gm);
+                        __syncwarp(gm);                                        // every lane has consumed the flags of these slots
                         cdot[q + mine] = total;                                // lanes sharing an index write the same value
                     }
                 } else {
@@ -596,8 +654,36 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB
                     if (ptn < p.P) {
                         const long long s = row * p.LP + (long long)lm * p.P + ptn;
                         grad_w0[s] = g_a[k];
-                        reinterpret_cast<float2*>(grad_loc)[s] = make_float2(g_x[k], g_y[k]);
+                        if constexpr (!FUSED) reinterpret_cast<float2*>(grad_loc)[s] = make_float2(g_x[k], g_y[k]);
                     }
+                }
+            }
+            if constexpr (FUSED) {
+                // chain the per-point location gradients to the level's box (cx, cy, w, h) and angle:
+                //   loc = (c + R u) * vr,  u = k * relu(size)   (box_attention.py:207-212, :321-336)
+                float bcx = 0.f, bcy = 0.f, bw = 0.f, bh = 0.f, ba = 0.f;
+#pragma unroll
+                for (int k = 0; k < PPL; ++k) {
+                    const int ptn = slane + k * SUB;
+                    if (lact && ptn < p.P) {
+                        const float2 kk = __ldg(reinterpret_cast<const float2*>(p.kidx) + ptn);
+                        const float gx = g_x[k] * lbx.vx, gy = g_y[k] * lbx.vy;
+                        const float ux = kk.x * lbx.sx, uy = kk.y * lbx.sy;
+                        bcx += gx;
+                        bcy += gy;
+                        bw += kk.x * (gx * lbx.cs + gy * lbx.sn);
+                        bh += kk.y * (gy * lbx.cs - gx * lbx.sn);
+                        ba += gx * (-ux * lbx.sn - uy * lbx.cs) + gy * (ux * lbx.cs - uy * lbx.sn);
+                    }
+                }
+                bcx = ssum<SUB>(bcx, gm); bcy = ssum<SUB>(bcy, gm);
+                bw = ssum<SUB>(bw, gm); bh = ssum<SUB>(bh, gm);
+                if (p.grad_angles) ba = ssum<SUB>(ba, gm);
+                if (lact && slane == 0) {
+                    const long long rl = row * p.L + lm;
+                    reinterpret_cast<float4*>(p.grad_boxes)[rl] =
+                        make_float4(bcx, bcy, lbx.pos_w ? bw : 0.f, lbx.pos_h ? bh : 0.f);
+                    if (p.grad_angles) static_cast<float*>(p.grad_angles)[rl] = ba;
                 }
             }
         }

@@ -254,3 +254,96 @@ def instance_attn_backward(value, spatial_shapes, level_start_index, sampling_lo
             ws.data_ptr() if ws is not None else None, ws_bytes, flags, _stream(value.device))
     _native.check(st, "instance_attn_backward")
     return [grad_value, grad_loc, grad_sw, grad_lw]
+
+
+# ------------------------------------------------- fused box -> grid -> attention
+def _fused_geometry(value, shapes, lsi, boxes, angles, valid_ratios, kernel_indices, attn):
+    for t, n in ((value, "value"), (shapes, "spatial_shapes"), (lsi, "level_start_index"), (boxes, "boxes"),
+                 (kernel_indices, "kernel_indices"), (attn, "attn_weight")):
+        _check_input(t, n)
+    if value.dim() != 4:
+        raise RuntimeError(f"value must be (B, S, heads, head_dim), got {tuple(value.shape)}")
+    if shapes.dtype != torch.int64 or lsi.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64")
+    B, S, H, D = value.shape
+    L = shapes.shape[0]
+    if boxes.dim() != 5 or boxes.shape[0] != B or boxes.shape[2] != H or boxes.shape[3] != L or boxes.shape[4] != 4:
+        raise RuntimeError(f"boxes must be (B={B}, Nq, heads={H}, L={L}, 4), got {tuple(boxes.shape)}")
+    Nq = boxes.shape[1]
+    if kernel_indices.dim() != 2 or kernel_indices.shape[1] != 2:
+        raise RuntimeError(f"kernel_indices must be (P, 2), got {tuple(kernel_indices.shape)}")
+    P = kernel_indices.shape[0]
+    if attn.numel() != B * Nq * H * L * P:
+        raise RuntimeError(f"attention weights must hold B*Nq*heads*L*P = {B * Nq * H * L * P} elements, got {tuple(attn.shape)}")
+    if angles is not None:
+        _check_input(angles, "angles")
+        if angles.numel() != B * Nq * H * L:
+            raise RuntimeError(f"angles must hold B*Nq*heads*L elements, got {tuple(angles.shape)}")
+    if valid_ratios is not None:
+        _check_input(valid_ratios, "valid_ratios")
+        if valid_ratios.numel() != B * L * 2:
+            raise RuntimeError(f"valid_ratios must hold B*L*2 elements, got {tuple(valid_ratios.shape)}")
+    if L > 32 or lsi.numel() != L:
+        raise RuntimeError("level_start_index must have one entry per level (at most 32 levels)")
+    return B, S, H, D, L, Nq, P
+
+
+def _aligned16(t):
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
+def box_grid_attn_forward(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios, kernel_indices,
+                          attn_weight, im2col_step=64):
+    """out = box_attn_forward(value, ..., grid(boxes, angles, valid_ratios, kernel_indices), attn_weight) with the
+    K x K grid of BoxAttention._where_to_attend (box_attention.py:196-214; rotated: :304-338) generated in-kernel."""
+    B, S, H, D, L, Nq, P = _fused_geometry(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios,
+                                           kernel_indices, attn_weight)
+    opt = tuple(t for t in (angles, valid_ratios) if t is not None)
+    suf, _ = _dtypes(value, boxes, (attn_weight, kernel_indices, *opt))
+    _step_check(B, im2col_step)
+    lib = _native.load()
+    value, boxes = _aligned16(value), _aligned16(boxes)
+    out = torch.empty((B, Nq, H * D), dtype=value.dtype, device=value.device)
+    with _on_device(value.device):
+        n = lib.bxr_box_grid_attn_workspace_bytes(value.element_size(), 0, B, S, H, D, L, Nq, P, _PATH_FLAGS)
+        ws = torch.empty(n, dtype=torch.uint8, device=value.device) if n else None
+        st = _fn(f"bxr_box_grid_attn_fwd_{suf}")(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), boxes.data_ptr(),
+            angles.data_ptr() if angles is not None else None,
+            valid_ratios.data_ptr() if valid_ratios is not None else None,
+            kernel_indices.data_ptr(), attn_weight.data_ptr(), B, S, H, D, L, Nq, P, out.data_ptr(),
+            ws.data_ptr() if ws is not None else None, n, _PATH_FLAGS, _stream(value.device))
+    _native.check(st, "box_grid_attn_forward")
+    return out
+
+
+def box_grid_attn_backward(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios, kernel_indices,
+                           attn_weight, grad_output, im2col_step=64):
+    """-> [grad_value, grad_boxes, grad_angles | None, grad_attn_weight]"""
+    B, S, H, D, L, Nq, P = _fused_geometry(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios,
+                                           kernel_indices, attn_weight)
+    opt = tuple(t for t in (angles, valid_ratios) if t is not None)
+    suf, _ = _dtypes(value, boxes, (attn_weight, kernel_indices, *opt))
+    _check_input(grad_output, "grad_output")
+    if grad_output.dtype != value.dtype or grad_output.numel() != B * Nq * H * D:
+        raise RuntimeError("grad_output must match the forward output's dtype and size")
+    _step_check(B, im2col_step)
+    lib = _native.load()
+    flags = (FLAG_DETERMINISTIC if deterministic() else 0) | _PATH_FLAGS
+    value, boxes, grad_output = _aligned16(value), _aligned16(boxes), _aligned16(grad_output)
+    grad_value = torch.empty_like(value)
+    grad_boxes = torch.empty_like(boxes)
+    grad_angles = torch.empty_like(angles) if angles is not None else None
+    grad_attn = torch.empty_like(attn_weight)
+    with _on_device(value.device):
+        n = lib.bxr_box_grid_attn_workspace_bytes(value.element_size(), 1, B, S, H, D, L, Nq, P, flags)
+        ws = torch.empty(n, dtype=torch.uint8, device=value.device) if n else None
+        st = _fn(f"bxr_box_grid_attn_bwd_{suf}")(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), boxes.data_ptr(),
+            angles.data_ptr() if angles is not None else None,
+            valid_ratios.data_ptr() if valid_ratios is not None else None,
+            kernel_indices.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(), B, S, H, D, L, Nq, P,
+            grad_value.data_ptr(), grad_boxes.data_ptr(), grad_angles.data_ptr() if grad_angles is not None else None,
+            grad_attn.data_ptr(), ws.data_ptr() if ws is not None else None, n, flags, _stream(value.device))
+    _native.check(st, "box_grid_attn_backward")
+    return [grad_value, grad_boxes, grad_angles, grad_attn]

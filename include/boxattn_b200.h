@@ -115,6 +115,40 @@ BXR_DECLARE_OPS(f32, float, float)
 BXR_DECLARE_OPS(f64, double, double)
 BXR_DECLARE_OPS(bf16, bxr_bf16, float)
 
+/*
+ * Fused box -> grid -> attention (beyond the reference's native surface).
+ * Replaces BoxAttention._where_to_attend (e2edet/module/box_attention.py:196-214) and the rotated
+ * variant of Box3dAttention (:304-338) *plus* box_attn_forward/backward: the K x K sampling grid
+ *     loc[b,q,h,l,p] = (centre + R(angle) (kernel_index_p * relu(size))) * valid_ratio[b,l]
+ * is generated inside the kernel, and the backward returns the gradient w.r.t. the boxes / angles
+ * instead of a (B,Nq,H,L,P,2) location gradient.
+ *   boxes          (B, Nq, H, L, 4)  cx, cy, w, h   (= ref_windows + offset/8 * ref_wh, computed by the caller)
+ *   angles         (B, Nq, H, L)     radians, or NULL (no rotation)
+ *   valid_ratios   (B, L, 2)         (x, y), or NULL
+ *   kernel_indices (P, 2)            the module's buffer
+ * Workspace: bxr_box_grid_attn_workspace_bytes() (used when a shape falls outside the fused kernels
+ * and the grid has to be materialised internally, and by the _bf16 / deterministic backward).
+ */
+size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H, int D, int L, int Nq, int P,
+                                         unsigned flags);
+
+#define BXR_DECLARE_FUSED(SUF, TV, TW)                                                                          \
+    int bxr_box_grid_attn_fwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,          \
+                                    const TW* boxes, const TW* angles, const TW* valid_ratios,                   \
+                                    const TW* kernel_indices, const TW* attn,                                    \
+                                    int B, int S, int H, int D, int L, int Nq, int P, TV* out,                   \
+                                    void* workspace, size_t workspace_bytes, unsigned flags, bxr_stream_t stream); \
+    int bxr_box_grid_attn_bwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,          \
+                                    const TW* boxes, const TW* angles, const TW* valid_ratios,                   \
+                                    const TW* kernel_indices, const TW* attn, const TV* grad_out,                \
+                                    int B, int S, int H, int D, int L, int Nq, int P,                            \
+                                    TV* grad_value, TW* grad_boxes, TW* grad_angles, TW* grad_attn,              \
+                                    void* workspace, size_t workspace_bytes, unsigned flags, bxr_stream_t stream);
+
+BXR_DECLARE_FUSED(f32, float, float)
+BXR_DECLARE_FUSED(f64, double, double)
+BXR_DECLARE_FUSED(bf16, bxr_bf16, float)
+
 #ifdef __cplusplus
 }
 #endif

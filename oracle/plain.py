@@ -93,3 +93,22 @@ def plain_instance_attn(value, shapes, grid, spatial_weights, level_weights, mas
     # (B,Nq,H,D,P) -> (B,Nq,K,K,H*D)
     mask = mask.permute(0, 1, 4, 2, 3).reshape(B, Nq, K, K, -1)
     return out, mask
+
+
+def grid_from_boxes(boxes, angles, valid_ratios, kernel_indices):
+    """The K x K sampling grid the reference modules build from boxes (TEST INFRASTRUCTURE ONLY).
+
+    Restates ``BoxAttention._where_to_attend`` (/root/reference/e2edet/module/box_attention.py:207-212)
+    and the rotated variant of ``Box3dAttention`` (:321-336) from the point where ``boxes`` / ``angles``
+    are known: boxes (B,Nq,H,L,4) cx,cy,w,h; angles (B,Nq,H,L,1) radians or None; valid_ratios
+    (B,1,1,L,1,2) or None; kernel_indices (P,2).  Returns (B,Nq,H,L,P,2) in [0,1] coordinates."""
+    center, size = boxes.unsqueeze(-2).split(2, dim=-1)
+    grid = kernel_indices * torch.relu(size)
+    if angles is not None:
+        cos_a, sin_a = torch.cos(angles), torch.sin(angles)
+        rot = torch.stack([cos_a, -sin_a, sin_a, cos_a], dim=-1).view(*angles.shape[:4], 1, 2, 2)
+        grid = (grid.unsqueeze(-2) * rot).sum(-1)
+    grid = center + grid
+    if valid_ratios is not None:
+        grid = grid * valid_ratios
+    return grid

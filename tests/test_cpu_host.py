@@ -18,10 +18,12 @@ def _header_symbols():
     text = open(os.path.join(ROOT, "include", "boxattn_b200.h")).read()
     names = set(re.findall(r"\b(bxr_[a-z0-9_]+)\s*\(", text))
     names -= {n for n in names if n.endswith("_")}           # macro stems: bxr_box_attn_fwd_##SUF
-    for op in ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd"):
-        for suf in re.findall(r"BXR_DECLARE_OPS\((\w+),", text):
-            if suf != "SUF":
-                names.add(f"bxr_{op}_{suf}")
+    for macro, ops in (("BXR_DECLARE_OPS", ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd")),
+                       ("BXR_DECLARE_FUSED", ("box_grid_attn_fwd", "box_grid_attn_bwd"))):
+        for op in ops:
+            for suf in re.findall(macro + r"\((\w+),", text):
+                if suf != "SUF":
+                    names.add(f"bxr_{op}_{suf}")
     return sorted(names)
 
 
@@ -30,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     _native.build()
     lib = _native.load()
     declared = _header_symbols()
-    assert len(declared) >= 17, declared
+    assert len(declared) >= 24, declared
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/boxattn_b200.h but not exported"
     assert set(_native.EXPORTS) == set(declared)

@@ -1,0 +1,178 @@
+"""GPU: the fused box -> grid -> attention op vs the reference formulation.
+
+Oracle = the reference's grid construction (BoxAttention._where_to_attend, box_attention.py:196-214;
+Box3dAttention, :304-338 -- restated in oracle/plain.py:grid_from_boxes) followed by its grid_sample
+oracle, differentiated by autograd in fp64.  Also: the three nn.Modules with set_fused_grid(True)
+against outputs of the reference's own module classes (tests/golden/modules_golden.npz).
+"""
+import math
+
+import pytest
+import torch
+
+from tests import helpers, refinputs
+from tests.test_gpu_ops import _near_cell_boundary
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _case(name):
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    cfg = {
+        # name: (B, shapes, H, D, Nq, K, rotation, valid_ratios, index divisor)
+        "enc_like_K4": (1, [(23, 30), (12, 15), (6, 8), (3, 4)], 8, 32, 200, 4, False, False, 4),
+        "k2_ratios": (2, [(20, 24), (10, 12), (5, 6)], 4, 32, 61, 2, False, True, 2),
+        "rot_k3_1lvl": (2, [(40, 40)], 8, 16, 77, 3, True, False, 2),
+        "rot_k2_ratios_d64": (1, [(16, 20), (8, 10)], 4, 64, 33, 2, True, True, 2),
+        "odd_d30_k2": (1, [(9, 7), (5, 4)], 2, 30, 9, 2, True, True, 2),        # generic path: grid materialised inside
+        "k6_p36": (1, [(30, 30), (15, 15)], 8, 32, 50, 6, False, False, 6),       # P = 36 > 4*G: falls back inside
+        "neg_sizes": (1, [(12, 12)], 4, 32, 40, 2, False, False, 2),
+    }[name]
+    B, shapes, H, D, Nq, K, rot, ratios, div = cfg
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    sh = refinputs.shapes_tensor(shapes)
+    start = refinputs.level_start_index(sh)
+    value = torch.rand(B, S, H, D, generator=g, dtype=torch.float64) * 2 - 1
+    boxes = torch.rand(B, Nq, H, L, 4, generator=g, dtype=torch.float64)
+    boxes[..., :2] = 0.05 + 0.9 * boxes[..., :2]
+    boxes[..., 2:] = 0.02 + 0.4 * boxes[..., 2:]
+    if name == "neg_sizes":
+        boxes[..., 2:] -= 0.15          # some widths / heights <= 0: relu and its zero gradient
+    angles = (torch.rand(B, Nq, H, L, 1, generator=g, dtype=torch.float64) * 2 * math.pi) if rot else None
+    vr = (0.6 + 0.4 * torch.rand(B, 1, 1, L, 1, 2, generator=g, dtype=torch.float64)) if ratios else None
+    half = K / 2.0
+    ticks = torch.linspace(-half + 0.5, half - 0.5, K, dtype=torch.float64) if K % 2 == 0 else \\
+        torch.linspace(-(K - 1) // 2, (K - 1) // 2, K, dtype=torch.float64)
+    yy, xx = torch.meshgrid(ticks, ticks, indexing="ij")
+    kidx = torch.stack([xx, yy], -1).reshape(-1, 2) / div
+    attn = torch.softmax(torch.randn(B, Nq, H, L * K * K, generator=g, dtype=torch.float64), -1).view(B, Nq, H, L, K, K)
+    go = torch.randn(B, Nq, H * D, generator=g, dtype=torch.float64)
+    return dict(value=value, shapes=sh, start=start, boxes=boxes, angles=angles, vr=vr, kidx=kidx, attn=attn, go=go)
+
+
+def _oracle(c):
+    from oracle import plain
+    value = c["value"].clone().requires_grad_(True)
+    boxes = c["boxes"].clone().requires_grad_(True)
+    angles = c["angles"].clone().requires_grad_(True) if c["angles"] is not None else None
+    attn = c["attn"].clone().requires_grad_(True)
+    grid = plain.grid_from_boxes(boxes, angles, c["vr"], c["kidx"])
+    B, S = value.shape[:2]
+    out = plain.plain_box_attn(value.view(B, S, -1), c["shapes"], 2 * grid - 1, attn)
+    out.backward(c["go"])
+    return out.detach(), grid.detach(), (value.grad, boxes.grad, angles.grad if angles is not None else None, attn.grad)
+
+
+def _ours(c, dtype, deterministic=False):
+    import boxer_b200
+    tw = torch.float64 if dtype == torch.float64 else torch.float32
+    mv = lambda t, dt: None if t is None else t.to(DEV, dt).contiguous()
+    value = mv(c["value"], dtype).requires_grad_(True)
+    boxes = mv(c["boxes"], tw).requires_grad_(True)
+    angles = mv(c["angles"], tw)
+    if angles is not None:
+        angles.requires_grad_(True)
+    attn = mv(c["attn"], tw).requires_grad_(True)
+    boxer_b200.set_deterministic(deterministic)
+    try:
+        fn = boxer_b200.BoxGridAttnBf16Function if dtype == torch.bfloat16 else boxer_b200.BoxGridAttnFunction
+        out = fn.apply(value, c["shapes"].to(DEV), c["start"].to(DEV), boxes, angles, mv(c["vr"], tw), mv(c["kidx"], tw), attn, 64)
+        out.backward(mv(c["go"], out.dtype))
+    finally:
+        boxer_b200.set_deterministic(None)
+    return out.detach(), (value.grad, boxes.grad, angles.grad if angles is not None else None, attn.grad)
+
+
+CASES = ["enc_like_K4", "k2_ratios", "rot_k3_1lvl", "rot_k2_ratios_d64", "odd_d30_k2", "k6_p36", "neg_sizes"]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4), (torch.bfloat16, 1e-2)],
+                         ids=["f64", "f32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_fused_matches_reference_formulation(name, dtype, tol):
+    c = _case(name)
+    if dtype == torch.bfloat16:
+        c["value"] = c["value"].bfloat16().double()
+        c["go"] = c["go"].bfloat16().double()
+    ref_out, grid, ref_g = _oracle(c)
+    out, g = _ours(c, dtype)
+    assert helpers.rel_err(out, ref_out) <= tol, "out"
+    assert helpers.rel_err(g[0], ref_g[0]) <= tol, "grad_value"
+    assert helpers.rel_err(g[3], ref_g[3]) <= tol, "grad_attn"
+    # box / angle gradients sum the location gradients of the level's points; a point that sits on a pixel
+    # grid line has a discontinuous d/dloc (fp32 may pick the other cell): compare levels without such points
+    if dtype == torch.float64:
+        assert helpers.rel_err(g[1], ref_g[1]) <= tol, "grad_boxes"
+        if ref_g[2] is not None:
+            assert helpers.rel_err(g[2], ref_g[2]) <= tol, "grad_angles"
+    else:
+        keep = (~_near_cell_boundary(grid, c["shapes"]).any(-1))[..., None]      # (B,Nq,H,L,1)
+        assert float(keep.double().mean()) > 0.8
+        gb, rb = g[1].double().cpu() * keep, ref_g[1] * keep
+        assert helpers.rel_err(gb, rb) <= tol, "grad_boxes"
+        if ref_g[2] is not None:
+            assert helpers.rel_err(g[2].double().cpu() * keep, ref_g[2] * keep) <= tol, "grad_angles"
+
+
+def test_fused_equals_unfused_on_the_same_device():
+    """grid materialised with torch + BoxAttnFunction vs the fused op: same kernels underneath (fp32)."""
+    import boxer_b200
+    from oracle import plain
+    c = _case("enc_like_K4")
+    out_f, g_f = _ours(c, torch.float32)
+    dev = lambda t: None if t is None else t.to(DEV, torch.float32)
+    value = dev(c["value"]).requires_grad_(True)
+    boxes = dev(c["boxes"]).requires_grad_(True)
+    attn = dev(c["attn"]).requires_grad_(True)
+    grid = plain.grid_from_boxes(boxes, None, None, dev(c["kidx"])).contiguous()
+    out = boxer_b200.BoxAttnFunction.apply(value, c["shapes"].to(DEV), c["start"].to(DEV), grid, attn, 64)
+    out.backward(dev(c["go"]))
+    assert helpers.rel_err(out_f, out.detach()) <= 2e-5
+    assert helpers.rel_err(g_f[0], value.grad) <= 2e-5
+    assert helpers.rel_err(g_f[3], attn.grad) <= 2e-5
+
+
+def test_fused_deterministic_and_paths_agree():
+    import boxer_b200
+    c = _case("rot_k2_ratios_d64")
+    a = _ours(c, torch.float32, deterministic=True)
+    b = _ours(c, torch.float32, deterministic=True)
+    assert all(torch.equal(x, y) for x, y in zip(a[1], b[1]) if x is not None)
+    boxer_b200.ops.set_kernel_path("point")            # grid materialised inside + point kernels
+    try:
+        p = _ours(c, torch.float32)
+    finally:
+        boxer_b200.ops.set_kernel_path("auto")
+    assert helpers.rel_err(a[0], p[0]) <= 2e-5
+    assert helpers.rel_err(a[1][0], p[1][0]) <= 2e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4)], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", ["box_3d_refs_masked", "box_4d_refs_k3", "inst_infer", "box3d_rot", "box3d_norot_4d"])
+def test_modules_with_fused_grid_match_reference_modules(case, dtype, tol):
+    import boxer_b200
+    spec = refinputs.module_cases()[case]
+    gold = helpers.golden("modules_golden")[case]
+    mod = getattr(boxer_b200, spec["cls"])(**spec["ctor"]).double()
+    state = {k[len("param_"):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("param_")}
+    mod.load_state_dict(state, strict=True)
+    mod = mod.to(DEV, dtype)
+    if spec["cls"] == "InstanceAttention":
+        mod.inferencing = spec["inferencing"]
+    args = [a.to(DEV, dtype) if (torch.is_tensor(a) and a.is_floating_point()) else (a.to(DEV) if torch.is_tensor(a) else a)
+            for a in refinputs.module_inputs(spec)]
+    boxer_b200.set_fused_grid(True)
+    try:
+        outs = mod(*args)
+    finally:
+        boxer_b200.set_fused_grid(False)
+    flat = []
+    for o in outs:
+        if o is None:
+            continue
+        flat.extend(o if isinstance(o, tuple) else [o])
+    assert len(flat) == int(gold["n_out"])
+    for i, o in enumerate(flat):
+        assert helpers.rel_err(o, gold[f"out{i}"]) <= tol, (case, i)
