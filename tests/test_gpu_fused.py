@@ -18,7 +18,7 @@ DEV = "cuda"
 
 
 def _case(name):
-    g = torch.Generator().manual_seed(hash(name) % 1000)
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
     cfg = {
         # name: (B, shapes, H, D, Nq, K, rotation, valid_ratios, index divisor)
         "enc_like_K4": (1, [(23, 30), (12, 15), (6, 8), (3, 4)], 8, 32, 200, 4, False, False, 4),
@@ -43,8 +43,10 @@ def _case(name):
     angles = (torch.rand(B, Nq, H, L, 1, generator=g, dtype=torch.float64) * 2 * math.pi) if rot else None
     vr = (0.6 + 0.4 * torch.rand(B, 1, 1, L, 1, 2, generator=g, dtype=torch.float64)) if ratios else None
     half = K / 2.0
-    ticks = torch.linspace(-half + 0.5, half - 0.5, K, dtype=torch.float64) if K % 2 == 0 else \\
-        torch.linspace(-(K - 1) // 2, (K - 1) // 2, K, dtype=torch.float64)
+    if K % 2 == 0:
+        ticks = torch.linspace(-half + 0.5, half - 0.5, K, dtype=torch.float64)
+    else:
+        ticks = torch.linspace(-(K - 1) // 2, (K - 1) // 2, K, dtype=torch.float64)
     yy, xx = torch.meshgrid(ticks, ticks, indexing="ij")
     kidx = torch.stack([xx, yy], -1).reshape(-1, 2) / div
     attn = torch.softmax(torch.randn(B, Nq, H, L * K * K, generator=g, dtype=torch.float64), -1).view(B, Nq, H, L, K, K)
