@@ -389,6 +389,32 @@ def variants(ops, dev, bw_peak):
     ops.set_deterministic(None)
     res["enc_K4_box_f32_deterministic"] = {"bwd_ms": tb}
 
+    # module level: BoxAttention (projections + softmax + grid + op) forward+backward, reference-style grid
+    # materialisation vs the fused box->grid op
+    import boxer_b200
+    S = w.value.shape[1]
+    for K in (2, 4):
+        torch.manual_seed(0)
+        mod = boxer_b200.BoxAttention(256, 4, 8, K).to(dev)
+        with torch.no_grad():
+            mod.linear_box_weight.normal_(0, 0.01)
+            mod.linear_attn_weight.normal_(0, 0.01)
+        q = torch.randn(1, S, 256, device=dev, requires_grad=True)
+        src = torch.randn(1, S, 256, device=dev, requires_grad=True)
+        refw = W.encoder_ref_windows(W.fpn_levels(), 1, dev)
+
+        def run_mod():
+            out, _ = mod(q, src, w.shapes, None, w.level_start, None, refw)
+            out.sum().backward()
+
+        r = {}
+        for fused in (False, True):
+            boxer_b200.set_fused_grid(fused)
+            r["fused_ms" if fused else "grid_ms"] = time_call(run_mod, reps=10)
+        boxer_b200.set_fused_grid(False)
+        r["speedup"] = r["grid_ms"] / r["fused_ms"]
+        res[f"module_BoxAttention_K{K}_fwdbwd"] = r
+
     # warm vs L2-flushed: one launch at a time, a 512 MB write in between evicts value / loc from L2
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
