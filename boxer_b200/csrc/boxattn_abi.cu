@@ -158,6 +158,14 @@ int dispatch_bwd_vec(int g, AttnParams& p, cudaStream_t st) {
     BXR_DISPATCH_G(g, (bwd_vec<TV, INSTANCE, ACC, G>(p, st)))
 }
 
+// bf16: lanes of 8 bytes (4 channels) when that gives the fp32 kernels' geometry (head_dim 32 -> G = 8)
+int bf16_lane8_group(int D) {
+    if (D % 8 == 0 && D / 8 == 8) return 0;        // head_dim 64: 16-byte lanes already give G = 8
+    if (D % 4) return 0;
+    const int g = D / 4;
+    return (g == 8 || g == 4 || g == 16) ? g : 0;
+}
+
 // ---- footprint-window kernels (boxattn_window.cuh): box op, enough rows to fill the GPU, P <= 4*G
 bool use_window(const AttnParams& p, int g, unsigned flags) {
     if (flags & BXR_FLAG_PATH_POINT) return false;
@@ -218,8 +226,8 @@ bool fused_applies(int dtype_bytes, int B, int S, int H, int D, int L, int P, un
     if (flags & BXR_FLAG_PATH_POINT) return false;
     if (dtype_bytes != 4 && dtype_bytes != 2) return false;
     const int vec = 16 / dtype_bytes;
-    if (D <= 0 || D % vec) return false;
-    const int g = D / vec;
+    int g = (D > 0 && D % vec == 0) ? D / vec : 0;
+    if (dtype_bytes == 2 && bf16_lane8_group(D)) g = bf16_lane8_group(D);
     if (g != 4 && g != 8 && g != 16) return false;
     if (P < 1 || P > 4 * g || (long long)L * P >= 65536) return false;
     if ((long long)B * S * g * H >= 0xffffffffLL) return false;
@@ -294,6 +302,15 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
     const int g = vec_group<TV>(D, p.LP);
     if (g && aligned16(value) && aligned16(out) && (!INSTANCE || aligned16(mask_out)) && aligned8(loc)) {
         if constexpr (!std::is_same<TV, double>::value) {
+            if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
+                if (const int g8 = bf16_lane8_group(D)) {
+                    if constexpr (!INSTANCE) {
+                        if (use_window(p, g8, flags)) return dispatch_fwd_win<bf16x4_t>(g8, p, st);
+                    } else {
+                        if (use_inst_own(p, g8, flags)) return g8 == 8 ? fwd_inst_own<bf16x4_t, 8>(p, st) : fwd_inst_own<bf16x4_t, 4>(p, st);
+                    }
+                }
+            }
             if constexpr (!INSTANCE) {
                 if (use_window(p, g, flags)) return dispatch_fwd_win<TV>(g, p, st);
             } else {
@@ -430,7 +447,25 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
         if constexpr (!INSTANCE) win = vec_ok && (fused ? true : use_window(p, g, flags));
         bool own = false;
         if constexpr (INSTANCE) own = vec_ok && use_inst_own(p, g, flags);
-        if (win) {
+        int g8 = 0;      // bf16 with 8-byte lanes
+        if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
+            g8 = vec_ok ? bf16_lane8_group(D) : 0;
+            if (g8) {
+                if constexpr (!INSTANCE) { if (fused || use_window(p, g8, flags)) win = true; else g8 = 0; }
+                else { if (use_inst_own(p, g8, flags)) own = true; else g8 = 0; }
+            }
+        }
+        if (win && g8) {
+            if constexpr (!INSTANCE) {
+                if (fused) status = det ? dispatch_bwd_win<bf16x4_t, long long, true>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float, true>(g8, p, st);
+                else status = det ? dispatch_bwd_win<bf16x4_t, long long>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float>(g8, p, st);
+            }
+        } else if (own && g8) {
+            if constexpr (INSTANCE) {
+                if (g8 == 8) status = det ? bwd_inst_own<bf16x4_t, 8, long long>(p, st) : bwd_inst_own<bf16x4_t, 8, float>(p, st);
+                else status = det ? bwd_inst_own<bf16x4_t, 4, long long>(p, st) : bwd_inst_own<bf16x4_t, 4, float>(p, st);
+            }
+        } else if (win) {
             if constexpr (!INSTANCE) {
                 if (fused) status = det ? dispatch_bwd_win<TV, long long, true>(g, p, st) : dispatch_bwd_win<TV, float, true>(g, p, st);
                 else status = det ? dispatch_bwd_win<TV, long long>(g, p, st) : dispatch_bwd_win<TV, float>(g, p, st);
@@ -519,6 +554,9 @@ int fused_forward(const TV* value, const int64_t* shapes, const int64_t* level_s
     const bool aligned = aligned16(value) && aligned16(out) && aligned16(boxes) && aligned8(kidx) && (!valid_ratios || aligned8(valid_ratios));
     if constexpr (!std::is_same<TV, double>::value) {
         if (aligned && fused_applies((int)sizeof(TV), B, S, H, D, L, P, flags)) {
+            if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
+                if (const int g8 = bf16_lane8_group(D)) return dispatch_fwd_win<bf16x4_t, true>(g8, p, st);
+            }
             const int g = vec_group<TV>(D, p.LP);
             return dispatch_fwd_win<TV, true>(g, p, st);
         }

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, 2) inst_fwd_own_kernel(const AttnPar
     const int split = gid & (nsplit - 1);
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;
     const long long HD = (long long)p.H * p.D;
-    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
+    const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
     const float* __restrict__ w1 = static_cast<const float*>(p.w1);
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 2) inst_bwd_own_kernel(const AttnPar
     const int split = gid & (nsplit - 1);
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;
     const long long HD = (long long)p.H * p.D;
-    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
+    const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
     const float* __restrict__ w1 = static_cast<const float*>(p.w1);

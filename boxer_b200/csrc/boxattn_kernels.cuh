@@ -92,8 +92,8 @@ template <> struct Vec16<float> {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
     // 16-byte-unit index off a uniform base: one IMAD.WIDE.U32 of address math per load
-    __device__ __forceinline__ static void load16(const uint4* base, unsigned idx, float (&v)[4]) {
-        const uint4 t = __ldg(base + idx);
+    __device__ __forceinline__ static void load16(const void* base, unsigned idx, float (&v)[4]) {
+        const uint4 t = __ldg(static_cast<const uint4*>(base) + idx);
         v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
     }
 };
@@ -108,8 +108,8 @@ template <> struct Vec16<__nv_bfloat16> {
             v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
         }
     }
-    __device__ __forceinline__ static void load16(const uint4* base, unsigned idx, float (&v)[8]) {
-        const uint4 t = __ldg(base + idx);
+    __device__ __forceinline__ static void load16(const void* base, unsigned idx, float (&v)[8]) {
+        const uint4 t = __ldg(static_cast<const uint4*>(base) + idx);
         const unsigned u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -125,6 +125,27 @@ template <> struct Vec16<__nv_bfloat16> {
             u[i] = *reinterpret_cast<const unsigned*>(&h);
         }
         *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+};
+
+// bf16 storage with 4 channels (8 bytes) per lane: for head_dim 32 this keeps G = 8 lanes per row --
+// the fp32 kernels' geometry (taps spread over 8 lanes, 4 rows per warp) at half the bytes per load.
+struct bf16x4_t { __nv_bfloat16 v; };
+template <> struct Vec16<bf16x4_t> {
+    static constexpr int VEC = 4;
+    __device__ __forceinline__ static void unpack(const uint2 t, float (&v)[4]) {
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    __device__ __forceinline__ static void load(const bf16x4_t* p, float (&v)[4]) {
+        unpack(__ldg(reinterpret_cast<const uint2*>(p)), v);
+    }
+    __device__ __forceinline__ static void load16(const void* base, unsigned idx, float (&v)[4]) {   // idx in 8-byte units
+        unpack(__ldg(static_cast<const uint2*>(base) + idx), v);
+    }
+    __device__ __forceinline__ static void store(bf16x4_t* p, const float (&v)[4]) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
     }
 };
 

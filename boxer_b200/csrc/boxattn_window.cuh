@@ -200,7 +200,7 @@ struct SubWin {
 // ------------------------------------------------------------------------------------------------
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
 template <typename TV, int G, int SUB, int PPL, bool FUSED>
-__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_FWD_MINB) box_fwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_MINB) box_fwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_FWD_MINB
     const unsigned gm = group_mask<G>();
     int* gwin = s_win + gid * kWinPitch;
     int* win = gwin + sub * CAP;
-    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in 16-byte units
-    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in lane chunks (VEC elements)
+    const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
 
@@ -421,7 +421,7 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
 }
 
 template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED>
-__global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB) box_bwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_MINB) box_bwd_win_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
@@ -441,8 +441,8 @@ __global__ void __launch_bounds__(kThreads, (sizeof(TV) == 2) ? 2 : BXR_BWD_MINB
     float* gdot = s_dot + gid * kWinPitch;
     int* win = gwin + sub * CAP;
     float* dot = gdot + sub * CAP;
-    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in 16-byte units
-    const uint4* __restrict__ value16 = static_cast<const uint4*>(p.value);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in lane chunks (VEC elements)
+    const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
     ACC* __restrict__ gacc = static_cast<ACC*>(p.grad_value_acc);
