@@ -303,11 +303,10 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
     if (g && aligned16(value) && aligned16(out) && (!INSTANCE || aligned16(mask_out)) && aligned8(loc)) {
         if constexpr (!std::is_same<TV, double>::value) {
             if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
-                if (const int g8 = bf16_lane8_group(D)) {
-                    if constexpr (!INSTANCE) {
+                // (measured, r01j: the instance kernels are faster with 16-byte lanes, so only the box op switches)
+                if constexpr (!INSTANCE) {
+                    if (const int g8 = bf16_lane8_group(D)) {
                         if (use_window(p, g8, flags)) return dispatch_fwd_win<bf16x4_t>(g8, p, st);
-                    } else {
-                        if (use_inst_own(p, g8, flags)) return g8 == 8 ? fwd_inst_own<bf16x4_t, 8>(p, st) : fwd_inst_own<bf16x4_t, 4>(p, st);
                     }
                 }
             }
@@ -449,21 +448,15 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
         if constexpr (INSTANCE) own = vec_ok && use_inst_own(p, g, flags);
         int g8 = 0;      // bf16 with 8-byte lanes
         if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
-            g8 = vec_ok ? bf16_lane8_group(D) : 0;
+            g8 = (vec_ok && !INSTANCE) ? bf16_lane8_group(D) : 0;
             if (g8) {
-                if constexpr (!INSTANCE) { if (fused || use_window(p, g8, flags)) win = true; else g8 = 0; }
-                else { if (use_inst_own(p, g8, flags)) own = true; else g8 = 0; }
+                if (fused || use_window(p, g8, flags)) win = true; else g8 = 0;
             }
         }
         if (win && g8) {
             if constexpr (!INSTANCE) {
                 if (fused) status = det ? dispatch_bwd_win<bf16x4_t, long long, true>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float, true>(g8, p, st);
                 else status = det ? dispatch_bwd_win<bf16x4_t, long long>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float>(g8, p, st);
-            }
-        } else if (own && g8) {
-            if constexpr (INSTANCE) {
-                if (g8 == 8) status = det ? bwd_inst_own<bf16x4_t, 8, long long>(p, st) : bwd_inst_own<bf16x4_t, 8, float>(p, st);
-                else status = det ? bwd_inst_own<bf16x4_t, 4, long long>(p, st) : bwd_inst_own<bf16x4_t, 4, float>(p, st);
             }
         } else if (win) {
             if constexpr (!INSTANCE) {
