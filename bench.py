@@ -468,6 +468,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
+    from boxer_b200 import _native
+    if _native.is_stale() and rank == 0:      # fresh checkout: compile the CUDA library first (no fallback exists)
+        _native.build()
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
     import boxer_b200
     from boxer_b200 import ops
     from boxer_b200 import workloads as W
