@@ -449,6 +449,42 @@ def test_all_out_of_range_and_nonfinite_locations():
     assert torch.equal(o1, o2) and bool(torch.isfinite(o1).all())
 
 
+def test_nonfinite_and_zero_weights_window_vs_point_paths():
+    """The window kernels accumulate pixel weights in fixed point; non-finite weights must still
+    propagate (they take the float path) and all-zero weights must give exact zeros, like the point kernels."""
+    from boxer_b200 import workloads as W
+    b = _ops()
+    w = W.coco_encoder(K=4, image=(72, 100), device=DEV)
+    attn = w.weights[0].clone()
+    attn[0, 3, 1, 0, 1, 2] = float("nan")
+    attn[0, 5, 2, 1, 0, 0] = float("inf")
+    attn[0, 7] = 0.0                       # a query whose weights are all exactly zero
+    attn[0, 9, 4, 2] = 0.0                 # one (row, level) with zero weights
+    attn[0, 11, 0, 0] *= -1.0              # negative weights are legal inputs
+    go = torch.randn(1, w.value.shape[1], 256, device=DEV)
+    res = {}
+    for path in ("window", "point"):
+        b.ops.set_kernel_path(path)
+        try:
+            out = b.ops.box_attn_forward(w.value, w.shapes, w.level_start, w.loc, attn, 64)
+            gv, gl, ga = b.ops.box_attn_backward(w.value, w.shapes, w.level_start, w.loc, attn, go, 64)
+        finally:
+            b.ops.set_kernel_path("auto")
+        res[path] = (out, gl, ga)
+        assert bool(torch.isnan(out[0, 3, 32:64]).all()) and bool(torch.isfinite(out[0, 3, :32]).all())
+        assert not bool(torch.isfinite(out[0, 5, 64:96]).any())
+        assert float(out[0, 7].abs().max()) == 0.0
+        assert float(gl[0, 7].abs().max()) == 0.0             # d out / d loc carries the weight as a factor
+        assert float(ga[0, 7].abs().max()) > 0.0              # d out / d attn does not
+    ow, op_ = res["window"][0], res["point"][0]
+    fin = torch.isfinite(op_)
+    assert torch.equal(torch.isfinite(ow), fin)
+    _close(ow[fin], op_[fin], 2e-5, "window vs point out")
+    gaw, gap = res["window"][2], res["point"][2]
+    fin = torch.isfinite(gap) & torch.isfinite(gaw)
+    _close(gaw[fin], gap[fin], 2e-5, "window vs point grad_attn")
+
+
 def test_border_semantics_match_grid_sample():
     """Half-pixel border: loc in (-0.5/W, 0) still gets weight from pixel 0 (window test is -1 < x)."""
     from oracle import plain
