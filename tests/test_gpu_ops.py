@@ -456,11 +456,12 @@ def test_nonfinite_and_zero_weights_window_vs_point_paths():
     b = _ops()
     w = W.coco_encoder(K=4, image=(72, 100), device=DEV)
     attn = w.weights[0].clone()
-    attn[0, 3, 1, 0, 1, 2] = float("nan")
-    attn[0, 5, 2, 1, 0, 0] = float("inf")
-    attn[0, 7] = 0.0                       # a query whose weights are all exactly zero
-    attn[0, 9, 4, 2] = 0.0                 # one (row, level) with zero weights
-    attn[0, 11, 0, 0] *= -1.0              # negative weights are legal inputs
+    # queries 58..62 = pixels (4, 6..10) of the 9 x 13 level 0: every sample point of theirs is inside
+    attn[0, 58, 1, 0, 1, 2] = float("nan")
+    attn[0, 59, 2, 1, 0, 0] = float("inf")
+    attn[0, 60] = 0.0                      # a query whose weights are all exactly zero
+    attn[0, 61, 4, 2] = 0.0                # one (row, level) with zero weights
+    attn[0, 62, 0, 0] *= -1.0              # negative weights are legal inputs
     go = torch.randn(1, w.value.shape[1], 256, device=DEV)
     res = {}
     for path in ("window", "point"):
@@ -471,11 +472,11 @@ def test_nonfinite_and_zero_weights_window_vs_point_paths():
         finally:
             b.ops.set_kernel_path("auto")
         res[path] = (out, gl, ga)
-        assert bool(torch.isnan(out[0, 3, 32:64]).all()) and bool(torch.isfinite(out[0, 3, :32]).all())
-        assert not bool(torch.isfinite(out[0, 5, 64:96]).any())
-        assert float(out[0, 7].abs().max()) == 0.0
-        assert float(gl[0, 7].abs().max()) == 0.0             # d out / d loc carries the weight as a factor
-        assert float(ga[0, 7].abs().max()) > 0.0              # d out / d attn does not
+        assert bool(torch.isnan(out[0, 58, 32:64]).all()) and bool(torch.isfinite(out[0, 58, :32]).all())
+        assert not bool(torch.isfinite(out[0, 59, 64:96]).any())
+        assert float(out[0, 60].abs().max()) == 0.0
+        assert float(gl[0, 60].abs().max()) == 0.0            # d out / d loc carries the weight as a factor
+        assert float(ga[0, 60].abs().max()) > 0.0             # d out / d attn does not
     ow, op_ = res["window"][0], res["point"][0]
     fin = torch.isfinite(op_)
     assert torch.equal(torch.isfinite(ow), fin)
