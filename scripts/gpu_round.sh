@@ -23,5 +23,14 @@ timeout 400 ncu --set full --clock-control none --import-source off -k "regex:at
     python scripts/prof_driver.py --workload enc --K 4 > $OUT/ncu_bwd.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source off -k "regex:attn_fwd_vec|box_fwd_win" -s 2 -c 1 -f -o $OUT/fwd_enc_K4_uniform \
     python scripts/prof_driver.py --workload enc --K 4 --dist uniform > $OUT/ncu_fwd_u.log 2>&1
+# the .ncu-rep files have grown past the 64 MiB copy-back limit: digest them here, keep only text
+for r in fwd_enc_K4 bwd_enc_K4 fwd_enc_K4_uniform; do
+  if [ -f $OUT/$r.ncu-rep ]; then
+    python scripts/ncu_summary.py $OUT/$r.ncu-rep > $OUT/$r.summary.txt 2>&1
+    ncu -i $OUT/$r.ncu-rep --page source --csv > $OUT/$r.source.csv 2>/dev/null
+    ncu -i $OUT/$r.ncu-rep --page details > $OUT/$r.details.txt 2>/dev/null
+    rm -f $OUT/$r.ncu-rep
+  fi
+done
 fi
 ls -la $OUT
