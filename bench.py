@@ -188,6 +188,27 @@ def kernel_times(ops, sets, reps):
     return statistics.mean(f_ms), statistics.mean(b_ms)
 
 
+def gpu_local_cpus(index):
+    """CPUs on the NUMA node the GPU hangs off (sysfs), or None.  Pinned host buffers are placed by first
+    touch, so the e2e leg runs its host side there: H2D / D2H then do not cross the socket interconnect."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus or None
+    except Exception:
+        return None
+
+
 def e2e_run(sets, steps, warmup, dist_on):
     """Public API with HOST buffers.  Every step: pinned host tensors -> H2D (value, loc, weights, grad_out)
     -> BoxAttnFunction.apply + backward -> D2H (out, grad_value, grad_loc, grad_attn).
@@ -504,7 +525,14 @@ def main():
         ms = timed(fn, args.steps, args.warmup, dist_on)
         n_launch = launches[0] - 2 * args.warmup      # kernels inside the timed region
         kf_ms, kb_ms = kernel_times(ops, sets, max(10, min(args.steps, 50)))
-        ms_e2e, h2d, d2h = e2e_run(sets, e2e_steps, 3, dist_on)
+        all_cpus = os.sched_getaffinity(0)
+        local = gpu_local_cpus(local_rank)
+        if local:
+            os.sched_setaffinity(0, local)
+        try:
+            ms_e2e, h2d, d2h = e2e_run(sets, e2e_steps, 5, dist_on)
+        finally:
+            os.sched_setaffinity(0, all_cpus)
     clocks = clk.summary()
     value = n_gpus * n_samples * args.steps / (ms * 1e-3) / 1e9
     e2e_val = n_gpus * n_samples * e2e_steps / (ms_e2e * 1e-3) / 1e9
@@ -534,6 +562,7 @@ def main():
         "roofline_step": {"achieved": ach_s, "frac": ach_s / bw_peak, "unit": "GB/s"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                "host_cpus": ("NUMA-local to the GPU: %d cpus" % len(local)) if local else "unpinned",
                 "path": "pinned host -> H2D -> BoxAttnFunction.apply + backward -> D2H(out, grad_value, grad_loc, grad_attn); "
                         "3 streams, double-buffered (upload i+1 / kernels i / download i-1 overlap)"},
         "gpu_launches": n_launch,
