@@ -599,3 +599,52 @@ def test_modules_match_reference_modules(case):
     assert len(flat) == int(gold["n_out"])
     for i, o in enumerate(flat):
         _close(o, gold[f"out{i}"], 1e-9, f"{case} out{i}")
+
+
+# ============================================================== runtime properties
+def test_cuda_graph_capture_and_replay():
+    """The library only enqueues work on the stream it is given (no allocation, no sync), so a
+    launch-bound decoder-sized forward+backward can be captured in a CUDA graph and replayed."""
+    from boxer_b200 import workloads as W
+    b = _ops()
+    w = W.coco_decoder(Nq=300, K=2, image=(200, 336), device=DEV)
+    go = torch.randn(1, 300, 256, device=DEV)
+    args = (w.value, w.shapes, w.level_start, w.loc, w.weights[0].contiguous())
+    ref_out = b.ops.box_attn_forward(*args, 64)                      # also warms the per-kernel occupancy cache
+    ref_g = b.ops.box_attn_backward(*args, go, 64)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            out = b.ops.box_attn_forward(*args, 64)
+            grads = b.ops.box_attn_backward(*args, go, 64)
+    torch.cuda.current_stream().wait_stream(s)
+    w.value.mul_(2.0)                                                # replay must see the new inputs
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(out, 2.0 * ref_out, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(grads[0], ref_g[0], rtol=1e-4, atol=1e-5)  # d/dvalue does not depend on value
+    assert torch.allclose(grads[2], 2.0 * ref_g[2], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_a_non_current_device():
+    """One process, tensors on cuda:1 while cuda:0 is current: the wrapper switches device for the call
+    (the reference has no device guard at all, box_attn.cu:56)."""
+    from boxer_b200 import workloads as W
+    b = _ops()
+    w0 = W.coco_encoder(K=4, image=(72, 100), device="cuda:0")
+    w1 = w0.to("cuda:1")
+    assert torch.cuda.current_device() == 0
+    out0 = b.ops.box_attn_forward(w0.value, w0.shapes, w0.level_start, w0.loc, w0.weights[0], 64)
+    out1 = b.ops.box_attn_forward(w1.value, w1.shapes, w1.level_start, w1.loc, w1.weights[0], 64)
+    assert out1.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(out0.cpu(), out1.cpu())
+    go = torch.randn_like(out0)
+    g0 = b.ops.box_attn_backward(w0.value, w0.shapes, w0.level_start, w0.loc, w0.weights[0], go, 64)
+    g1 = b.ops.box_attn_backward(w1.value, w1.shapes, w1.level_start, w1.loc, w1.weights[0], go.to("cuda:1"), 64)
+    assert torch.equal(g0[1].cpu(), g1[1].cpu()) and torch.equal(g0[2].cpu(), g1[2].cpu())
+    with pytest.raises(RuntimeError, match="same device"):
+        b.ops.box_attn_forward(w0.value, w1.shapes, w0.level_start, w0.loc, w0.weights[0], 64)
