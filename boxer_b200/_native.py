@@ -27,8 +27,12 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--compiler-options", "-fPIC",
-    "-shared",
 ]
+# boxattn_abi.cu is compiled once per (dtype, direction) slice, in parallel, and the objects are linked into one
+# library (the BXR_TU_* macros at the top of that file); compiled without -D it is one complete translation unit.
+SLICES = [("common", 0, 0, 1)] + [(f"{dt}_{dn}", db, dd, 0)
+                                  for dt, db in (("f32", 1), ("f64", 2), ("bf16", 4))
+                                  for dn, dd in (("fwd", 1), ("bwd", 2))]
 
 DTYPES = ("f32", "f64", "bf16")
 OPS = ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd")
@@ -63,16 +67,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and not is_stale():
             return LIB_PATH
         os.makedirs(LIB_DIR, exist_ok=True)
+        objdir = os.path.join(ROOT, "build", "boxattn_b200")
+        os.makedirs(objdir, exist_ok=True)
+        nvcc = _nvcc()
+        procs = []
+        for name, dtypes, dirs, common in SLICES:
+            obj = os.path.join(objdir, name + ".o")
+            cmd = [nvcc, *NVCC_FLAGS, f"-DBXR_TU_DTYPES={dtypes}", f"-DBXR_TU_DIRS={dirs}", f"-DBXR_TU_COMMON={common}", f"-DBXR_TU_NAME={name}",
+                   "-c", "-o", obj, *SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd))
+            procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        logs, failed = [], False
+        for obj, proc in procs:
+            out, _ = proc.communicate()
+            logs.append(out)
+            failed |= proc.returncode != 0
+        if failed:
+            raise RuntimeError("nvcc failed:\n" + "\n".join(logs))
+        if verbose:
+            print("\n".join(logs))
         tmp = LIB_PATH + ".tmp"
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *SOURCES]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd))
-        proc = subprocess.run(cmd, capture_output=True, text=True)
-        if proc.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-        if verbose:
-            print(proc.stderr)
+        link = subprocess.run([nvcc, "-shared", "-o", tmp, *[o for o, _ in procs]], capture_output=True, text=True)
+        if link.returncode != 0:
+            raise RuntimeError("link failed:\n" + link.stdout + link.stderr)
         os.replace(tmp, LIB_PATH)
         return LIB_PATH
 

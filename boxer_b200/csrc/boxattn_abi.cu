@@ -14,12 +14,42 @@
 #include "boxattn_fused.cuh"
 #include "../../include/boxattn_b200.h"
 
-namespace {
+// Build-time slicing: the same source can be compiled once per (dtype, direction) slice, in parallel,
+// and the objects linked into one library (boxer_b200/_native.py); with no -D it is one complete TU.
+#ifndef BXR_TU_DTYPES
+#define BXR_TU_DTYPES 7     // bit set: 1 = f32, 2 = f64, 4 = bf16
+#endif
+#ifndef BXR_TU_DIRS
+#define BXR_TU_DIRS 3       // bit set: 1 = forward entry points, 2 = backward entry points
+#endif
+#ifndef BXR_TU_COMMON
+#define BXR_TU_COMMON 1     // the untyped entry points and the per-thread error state live in one slice
+#endif
 
-using namespace bxr;
-
+namespace bxr_host {
+// per-thread state behind bxr_last_error_detail() / bxr_last_launch_count(); shared by all slices
+extern thread_local char g_detail[256];
+extern thread_local int g_launches;
+#if BXR_TU_COMMON
 thread_local char g_detail[256] = "";
 thread_local int g_launches = 0;
+#endif
+}  // namespace bxr_host
+
+// nvcc gives functions of an unnamed namespace names derived from the file name, which collide between
+// slices of the same file: every slice gets its own named namespace instead
+#ifndef BXR_TU_NAME
+#define BXR_TU_NAME all
+#endif
+#define BXR_CAT2(a, b) a##b
+#define BXR_CAT(a, b) BXR_CAT2(a, b)
+#define BXR_SLICE_NS BXR_CAT(bxr_slice_, BXR_TU_NAME)
+
+namespace BXR_SLICE_NS {
+
+using namespace bxr;
+using bxr_host::g_detail;
+using bxr_host::g_launches;
 
 int fail(int status, const char* what) {
     snprintf(g_detail, sizeof(g_detail), "%s", what);
@@ -424,7 +454,7 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
             if (int s = absmax<TV>(grad_mask, p.rows * D * P, bits + 2, st)) return s;
             if (int s = absmax<TW>(w1, p.rows * p.LP, bits + 3, st)) return s;
         }
-        det_scale_kernel<<<1, 1, 0, st>>>(bits, scale);
+        det_scale_kernel<0><<<1, 1, 0, st>>>(bits, scale);
         BXR_CUDA(cudaGetLastError());
         ++g_launches;
         p.det_scale = scale;
@@ -626,10 +656,13 @@ int fused_backward(const TV* value, const int64_t* shapes, const int64_t* level_
     return BXR_OK;
 }
 
-}  // namespace
+}  // namespace BXR_SLICE_NS
+
+using namespace BXR_SLICE_NS;
 
 extern "C" {
 
+#if BXR_TU_COMMON
 int bxr_abi_version(void) { return BXR_ABI_VERSION; }
 
 const char* bxr_status_string(int status) {
@@ -652,21 +685,18 @@ size_t bxr_attn_bwd_workspace_bytes(int dtype_bytes, int B, int S, int H, int D,
     return workspace_bytes(dtype_bytes, (long long)B * S * H * D, flags);
 }
 
-#define BXR_DEFINE_OPS(SUF, TVABI, TV, TW)                                                                           \
+size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H, int D, int L, int Nq, int P,
+                                         unsigned flags) {
+    return fused_workspace_bytes(dtype_bytes, backward, B, S, H, D, L, Nq, P, flags);
+}
+#endif  // BXR_TU_COMMON
+
+#define BXR_DEFINE_OPS_FWD(SUF, TVABI, TV, TW)                                                                       \
     int bxr_box_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, \
                                const TW* attn, int B, int S, int H, int D, int L, int Nq, int P, TVABI* out,         \
                                unsigned flags, bxr_stream_t stream) {                                                \
         return forward<TV, TW, false>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, attn, nullptr,   \
                                       B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out), nullptr, flags, stream);     \
-    }                                                                                                                \
-    int bxr_box_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, \
-                               const TW* attn, const TVABI* grad_out, int B, int S, int H, int D, int L, int Nq,     \
-                               int P, TVABI* grad_value, TW* grad_loc, TW* grad_attn, void* workspace,               \
-                               size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {                        \
-        return backward<TV, TW, false>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, attn, nullptr,  \
-                                       reinterpret_cast<const TV*>(grad_out), nullptr, B, S, H, D, L, Nq, P,         \
-                                       reinterpret_cast<TV*>(grad_value), grad_loc, grad_attn, nullptr, workspace,   \
-                                       workspace_bytes, flags, stream);                                              \
     }                                                                                                                \
     int bxr_instance_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
                                     const TW* loc, const TW* spatial_w, const TW* level_w, int B, int S, int H,      \
@@ -675,6 +705,25 @@ size_t bxr_attn_bwd_workspace_bytes(int dtype_bytes, int B, int S, int H, int D,
         return forward<TV, TW, true>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, spatial_w,        \
                                      level_w, B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out),                      \
                                      reinterpret_cast<TV*>(mask_out), flags, stream);                                \
+    }                                                                                                                \
+    int bxr_box_grid_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
+                                    const TW* boxes, const TW* angles, const TW* valid_ratios, const TW* kidx,       \
+                                    const TW* attn, int B, int S, int H, int D, int L, int Nq, int P, TVABI* out,    \
+                                    void* workspace, size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {  \
+        return fused_forward<TV, TW>(reinterpret_cast<const TV*>(value), shapes, level_start, boxes, angles,         \
+                                     valid_ratios, kidx, attn, B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out),     \
+                                     workspace, workspace_bytes, flags, stream);                                     \
+    }
+
+#define BXR_DEFINE_OPS_BWD(SUF, TVABI, TV, TW)                                                                       \
+    int bxr_box_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, \
+                               const TW* attn, const TVABI* grad_out, int B, int S, int H, int D, int L, int Nq,     \
+                               int P, TVABI* grad_value, TW* grad_loc, TW* grad_attn, void* workspace,               \
+                               size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {                        \
+        return backward<TV, TW, false>(reinterpret_cast<const TV*>(value), shapes, level_start, loc, attn, nullptr,  \
+                                       reinterpret_cast<const TV*>(grad_out), nullptr, B, S, H, D, L, Nq, P,         \
+                                       reinterpret_cast<TV*>(grad_value), grad_loc, grad_attn, nullptr, workspace,   \
+                                       workspace_bytes, flags, stream);                                              \
     }                                                                                                                \
     int bxr_instance_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
                                     const TW* loc, const TW* spatial_w, const TW* level_w, const TVABI* grad_out,    \
@@ -686,25 +735,6 @@ size_t bxr_attn_bwd_workspace_bytes(int dtype_bytes, int B, int S, int H, int D,
                                       reinterpret_cast<const TV*>(grad_mask), B, S, H, D, L, Nq, P,                  \
                                       reinterpret_cast<TV*>(grad_value), grad_loc, grad_spatial_w, grad_level_w,     \
                                       workspace, workspace_bytes, flags, stream);                                    \
-    }
-
-BXR_DEFINE_OPS(f32, float, float, float)
-BXR_DEFINE_OPS(f64, double, double, double)
-BXR_DEFINE_OPS(bf16, bxr_bf16, __nv_bfloat16, float)
-
-size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H, int D, int L, int Nq, int P,
-                                         unsigned flags) {
-    return fused_workspace_bytes(dtype_bytes, backward, B, S, H, D, L, Nq, P, flags);
-}
-
-#define BXR_DEFINE_FUSED(SUF, TVABI, TV, TW)                                                                         \
-    int bxr_box_grid_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
-                                    const TW* boxes, const TW* angles, const TW* valid_ratios, const TW* kidx,       \
-                                    const TW* attn, int B, int S, int H, int D, int L, int Nq, int P, TVABI* out,    \
-                                    void* workspace, size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {  \
-        return fused_forward<TV, TW>(reinterpret_cast<const TV*>(value), shapes, level_start, boxes, angles,         \
-                                     valid_ratios, kidx, attn, B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out),     \
-                                     workspace, workspace_bytes, flags, stream);                                     \
     }                                                                                                                \
     int bxr_box_grid_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,           \
                                     const TW* boxes, const TW* angles, const TW* valid_ratios, const TW* kidx,       \
@@ -718,8 +748,28 @@ size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, i
                                       grad_attn, workspace, workspace_bytes, flags, stream);                         \
     }
 
-BXR_DEFINE_FUSED(f32, float, float, float)
-BXR_DEFINE_FUSED(f64, double, double, double)
-BXR_DEFINE_FUSED(bf16, bxr_bf16, __nv_bfloat16, float)
+#if BXR_TU_DIRS & 1
+#define BXR_FWD(...) BXR_DEFINE_OPS_FWD(__VA_ARGS__)
+#else
+#define BXR_FWD(...)
+#endif
+#if BXR_TU_DIRS & 2
+#define BXR_BWD(...) BXR_DEFINE_OPS_BWD(__VA_ARGS__)
+#else
+#define BXR_BWD(...)
+#endif
+
+#if BXR_TU_DTYPES & 1
+BXR_FWD(f32, float, float, float)
+BXR_BWD(f32, float, float, float)
+#endif
+#if BXR_TU_DTYPES & 2
+BXR_FWD(f64, double, double, double)
+BXR_BWD(f64, double, double, double)
+#endif
+#if BXR_TU_DTYPES & 4
+BXR_FWD(bf16, bxr_bf16, __nv_bfloat16, float)
+BXR_BWD(bf16, bxr_bf16, __nv_bfloat16, float)
+#endif
 
 }  // extern "C"

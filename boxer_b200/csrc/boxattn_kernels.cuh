@@ -664,6 +664,8 @@ __global__ void absmax_kernel(const T* __restrict__ x, long long n, unsigned* __
 
 // scale = 2^(40 - ceil(log2(bound))), bound = gmax0*wmax0 (+ gmax1*wmax1): every contribution
 // |cw*tg| <= bound maps below 2^40, leaving 2^23 worst-case contributions of headroom in int64.
+// (a template only so that the definition may appear in several translation units)
+template <int = 0>
 __global__ void det_scale_kernel(const unsigned* __restrict__ bits, float* __restrict__ scale) {
     const float g0 = __uint_as_float(bits[0]), a0 = __uint_as_float(bits[1]);
     const float g1 = __uint_as_float(bits[2]), a1 = __uint_as_float(bits[3]);
