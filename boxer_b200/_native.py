@@ -89,7 +89,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print("\n".join(logs))
         tmp = LIB_PATH + ".tmp"
-        link = subprocess.run([nvcc, "-shared", "-o", tmp, *[o for o, _ in procs]], capture_output=True, text=True)
+        link = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *[o for o, _ in procs]], capture_output=True, text=True)
         if link.returncode != 0:
             raise RuntimeError("link failed:\n" + link.stdout + link.stderr)
         os.replace(tmp, LIB_PATH)
