@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(_PKG, "_C")
 LIB_PATH = os.environ.get("BOXER_B200_LIB") or os.path.join(LIB_DIR, "libboxattn_b200.so")
 HEADER = os.path.join(ROOT, "include", "boxattn_b200.h")
 SOURCES = [os.path.join(CSRC, "boxattn_abi.cu")]
-DEPENDS = SOURCES + [os.path.join(CSRC, "boxattn_kernels.cuh"), os.path.join(CSRC, "boxattn_fused.cuh"), os.path.join(CSRC, "boxattn_window.cuh"), os.path.join(CSRC, "boxattn_instance.cuh"), HEADER]
+DEPENDS = SOURCES + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + [HEADER]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and not is_stale():
             return LIB_PATH
         os.makedirs(LIB_DIR, exist_ok=True)
-        objdir = os.path.join(ROOT, "build", "boxattn_b200")
+        objdir = os.path.join(os.environ.get("TMPDIR", "/tmp"), "boxattn_b200_build")   # objects stay out of the tree
         os.makedirs(objdir, exist_ok=True)
         nvcc = _nvcc()
         procs = []

@@ -12,6 +12,7 @@
 #include "boxattn_window.cuh"
 #include "boxattn_instance.cuh"
 #include "boxattn_fused.cuh"
+#include "boxattn_staged.cuh"
 #include "../../include/boxattn_b200.h"
 
 // Build-time slicing: the same source can be compiled once per (dtype, direction) slice, in parallel,
@@ -251,6 +252,54 @@ int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st) {
     BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC, FUSED>(p, st)))
 }
 
+// ---- staged-row kernels (boxattn_staged.cuh): the window algorithm with TMA-staged row operands.
+// Needs 16-byte granular rows (LP % 4 == 0) and operand pointers, and a shared-memory plan that
+// leaves at least two CTAs per SM.
+template <void (*K)(const AttnParams)>
+int launch_units_smem(const AttnParams& p, size_t smem, cudaStream_t st, const char* name) {
+    thread_local int cfg_dev = -1, cfg_occ = 0;
+    thread_local size_t cfg_smem = 0;
+    int dev = 0;
+    BXR_CUDA(cudaGetDevice(&dev));
+    if (dev != cfg_dev || smem != cfg_smem) {
+        BXR_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 0;
+        BXR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, kThreads, smem));
+        if (n <= 0) return fail(BXR_ERR_UNSUPPORTED, "staged kernel does not fit an SM");
+        cfg_dev = dev; cfg_smem = smem; cfg_occ = n;
+    }
+    int grid = sm_count() * cfg_occ;
+    if (grid > p.units) grid = p.units;
+    if (grid < 1) grid = 1;
+    K<<<grid, kThreads, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    ++g_launches;
+    return BXR_OK;
+}
+
+constexpr size_t kStgMaxSmem = 100 * 1024;
+
+bool use_staged(const AttnParams& p, int g, int mode, int stages, unsigned flags) {
+    // opt-in: measured on B200 (profiles/r01n_*) the staged forward equals the plain window kernel on the
+    // box-structured encoder workload (0.193 vs 0.195 ms) and is slower on uniform locations / 2x2 grids
+    if (!(flags & BXR_FLAG_STAGED) || (flags & BXR_FLAG_PATH_POINT)) return false;
+    if (p.LP % 4) return false;
+    if (!aligned16(p.w0) || !aligned16(mode == 0 ? p.loc : p.boxes)) return false;
+    return stg_plan(g, mode, p.L, p.LP, stages).total_bytes <= kStgMaxSmem;
+}
+
+template <typename TV, int G, int SUB, int PPL, int MODE>
+int fwd_stg(AttnParams& p, cudaStream_t st) {
+    p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
+    return launch_units_smem<box_fwd_stg_kernel<TV, G, SUB, PPL, MODE>>(p, stg_plan(G, MODE, p.L, p.LP, 1).total_bytes, st,
+                                                                         "box_fwd_stg_kernel");
+}
+template <typename TV, int MODE>
+int dispatch_fwd_stg(int g, AttnParams& p, cudaStream_t st) {
+    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_stg<TV, G, SUB, PPL, MODE>(p, st)))
+}
+
 // the fused (box -> grid) window kernels apply whenever the vector layout does; no row-count threshold
 bool fused_applies(int dtype_bytes, int B, int S, int H, int D, int L, int P, unsigned flags) {
     if (flags & BXR_FLAG_PATH_POINT) return false;
@@ -336,12 +385,15 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
                 // (measured, r01j: the instance kernels are faster with 16-byte lanes, so only the box op switches)
                 if constexpr (!INSTANCE) {
                     if (const int g8 = bf16_lane8_group(D)) {
-                        if (use_window(p, g8, flags)) return dispatch_fwd_win<bf16x4_t>(g8, p, st);
+                        if (use_window(p, g8, flags))
+                            return use_staged(p, g8, 0, 1, flags) ? dispatch_fwd_stg<bf16x4_t, 0>(g8, p, st)
+                                                                  : dispatch_fwd_win<bf16x4_t>(g8, p, st);
                     }
                 }
             }
             if constexpr (!INSTANCE) {
-                if (use_window(p, g, flags)) return dispatch_fwd_win<TV>(g, p, st);
+                if (use_window(p, g, flags))
+                    return use_staged(p, g, 0, 1, flags) ? dispatch_fwd_stg<TV, 0>(g, p, st) : dispatch_fwd_win<TV>(g, p, st);
             } else {
                 if (use_inst_own(p, g, flags)) return g == 8 ? fwd_inst_own<TV, 8>(p, st) : fwd_inst_own<TV, 4>(p, st);
             }
@@ -578,10 +630,12 @@ int fused_forward(const TV* value, const int64_t* shapes, const int64_t* level_s
     if constexpr (!std::is_same<TV, double>::value) {
         if (aligned && fused_applies((int)sizeof(TV), B, S, H, D, L, P, flags)) {
             if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
-                if (const int g8 = bf16_lane8_group(D)) return dispatch_fwd_win<bf16x4_t, true>(g8, p, st);
+                if (const int g8 = bf16_lane8_group(D))
+                    return use_staged(p, g8, 1, 1, flags) ? dispatch_fwd_stg<bf16x4_t, 1>(g8, p, st)
+                                                          : dispatch_fwd_win<bf16x4_t, true>(g8, p, st);
             }
             const int g = vec_group<TV>(D, p.LP);
-            return dispatch_fwd_win<TV, true>(g, p, st);
+            return use_staged(p, g, 1, 1, flags) ? dispatch_fwd_stg<TV, 1>(g, p, st) : dispatch_fwd_win<TV, true>(g, p, st);
         }
     }
     // general path: materialise the grid, then the location-taking op

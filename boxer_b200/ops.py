@@ -33,6 +33,7 @@ FLAG_DETERMINISTIC = 0x1
 
 FLAG_PATH_WINDOW = 0x2
 FLAG_PATH_POINT = 0x4
+FLAG_STAGED = 0x8
 _PATH_FLAGS = 0               # tuning / testing override of the kernel family (see set_kernel_path)
 
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
@@ -53,9 +54,12 @@ def deterministic() -> bool:
 
 def set_kernel_path(path: str = "auto"):
     """"auto" (default): footprint-window kernels for large box-attention calls, point kernels otherwise;
-    "window" / "point": force one family where it applies (A/B benchmarking and tests)."""
+    "window" / "point": force one family where it applies (A/B benchmarking and tests);
+    "staged" / "window-staged": the window forward with TMA-staged row operands and a pooled multi-level window
+    (experiment, boxattn_staged.cuh; measured no faster than the plain window kernels)."""
     global _PATH_FLAGS
-    _PATH_FLAGS = {"auto": 0, "window": FLAG_PATH_WINDOW, "point": FLAG_PATH_POINT}[path]
+    _PATH_FLAGS = {"auto": 0, "window": FLAG_PATH_WINDOW, "point": FLAG_PATH_POINT, "staged": FLAG_STAGED,
+                   "window-staged": FLAG_PATH_WINDOW | FLAG_STAGED}[path]
 
 
 def last_launch_count() -> int:

@@ -71,6 +71,9 @@ typedef enum bxr_status {
                                        even for row counts where the point-split kernels are the default */
 #define BXR_FLAG_PATH_POINT 0x4u    /* tuning/testing: never use the footprint-window kernels */
 
+#define BXR_FLAG_STAGED 0x8u        /* tuning/testing: footprint-window forward with TMA-staged row operands (cp.async.bulk
+                                       + mbarrier per warp) and a pooled multi-level window; see boxattn_staged.cuh */
+
 typedef void* bxr_stream_t;   /* a cudaStream_t */
 typedef uint16_t bxr_bf16;    /* raw bfloat16 bits */
 

@@ -20,13 +20,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def line_table(lib, kernel_sub):
     """offset -> (file, line) for the first function whose mangled name contains kernel_sub."""
-    tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+    # the library is linked from several objects whose cubins share one name (cuobjdump -xelf would overwrite
+    # them): `lib` may be a directory of .o files (boxer_b200/_native.py's object directory), one cubin each
+    files = [os.path.join(lib, f) for f in sorted(os.listdir(lib)) if f.endswith(".o")] if os.path.isdir(lib) else [lib]
+    cubins = []
+    for f in files:
+        tmp = tempfile.mkdtemp()
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(f)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+        cubins += [os.path.join(tmp, c) for c in os.listdir(tmp) if c.endswith(".cubin")]
     table = {}
-    for f in os.listdir(tmp):
-        if not f.endswith(".cubin"):
+    for f in cubins:
+        if kernel_sub.encode() not in open(f, "rb").read():
             continue
-        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        txt = subprocess.run(["nvdisasm", "-g", "-c", f], capture_output=True, text=True).stdout
         cur, inside, done = None, False, False
         for ln in txt.splitlines():
             if ln.startswith("//----") and ".text." in ln:
@@ -52,7 +58,7 @@ def line_table(lib, kernel_sub):
 
 def main():
     path, ksub = sys.argv[1], sys.argv[2]
-    lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "boxer_b200", "_C", "libboxattn_b200.so")
+    lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.environ.get("TMPDIR", "/tmp"), "boxattn_b200_build")
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     table = line_table(lib, ksub)
     rows = list(csv.reader(open(path)))

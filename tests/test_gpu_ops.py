@@ -295,8 +295,9 @@ def test_instance_mask_head_vs_oracle(K, Nq, dtype):
 
 # ============================================================== footprint-window kernels, forced at small sizes
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("path", ["window", "window-staged"])
 @pytest.mark.parametrize("case", ["enc_box_K4", "enc_box_K2", "enc_uniform_K4", "enc_box_K3_oob", "dec_K4", "bev_K3", "enc_box_K5"])
-def test_window_kernels_vs_oracle(case, dtype):
+def test_window_kernels_vs_oracle(case, dtype, path):
     """Same op through the footprint-window kernels (forced with set_kernel_path) on small inputs:
     window mode (box-structured), per-point fallback (uniform / wide boxes), borders and padding."""
     from boxer_b200 import workloads as W
@@ -318,7 +319,7 @@ def test_window_kernels_vs_oracle(case, dtype):
     go = torch.randn(B, Nq, C, device=DEV)
     if dtype == torch.bfloat16:
         go = go.bfloat16().float()
-    b.ops.set_kernel_path("window")
+    b.ops.set_kernel_path(path)
     try:
         out, grads = _run_box(_wl_inputs(w), dtype, go)
         det = _run_box(_wl_inputs(w), dtype, go, deterministic=True)[1]
@@ -464,7 +465,7 @@ def test_nonfinite_and_zero_weights_window_vs_point_paths():
     attn[0, 62, 0, 0] *= -1.0              # negative weights are legal inputs
     go = torch.randn(1, w.value.shape[1], 256, device=DEV)
     res = {}
-    for path in ("window", "point"):
+    for path in ("window", "window-staged", "point"):
         b.ops.set_kernel_path(path)
         try:
             out = b.ops.box_attn_forward(w.value, w.shapes, w.level_start, w.loc, attn, 64)
