@@ -11,15 +11,17 @@ Everything computes in ``boxer_b200/_C/libboxattn_b200.so`` (C ABI: include/boxa
 there is no CPU or PyTorch fallback.
 """
 from . import _native, compat, ops
-from .box_attention import (Box3dAttention, BoxAttention, InstanceAttention, set_amp_native, set_fused_grid)
+from .box_attention import (Box3dAttention, BoxAttention, InstanceAttention, set_amp_native, set_fused_grid,
+                            set_fused_softmax)
 from .box_attention_func import (BoxAttnBf16Function, BoxAttnFunction, BoxGridAttnBf16Function, BoxGridAttnFunction,
+                                 BoxGridSoftmaxAttnBf16Function, BoxGridSoftmaxAttnFunction,
                                  InstanceAttnBf16Function, InstanceAttnFunction)
 from .ops import set_deterministic
 
 __all__ = [
     "BoxAttnFunction", "InstanceAttnFunction", "BoxAttnBf16Function", "InstanceAttnBf16Function",
     "BoxAttention", "InstanceAttention", "Box3dAttention",
-    "BoxGridAttnFunction", "BoxGridAttnBf16Function",
-    "ops", "compat", "set_deterministic", "set_amp_native", "set_fused_grid",
+    "BoxGridAttnFunction", "BoxGridAttnBf16Function", "BoxGridSoftmaxAttnFunction", "BoxGridSoftmaxAttnBf16Function",
+    "ops", "compat", "set_deterministic", "set_amp_native", "set_fused_grid", "set_fused_softmax",
 ]
 __version__ = "0.1.0"

@@ -36,7 +36,7 @@ SLICES = [("common", 0, 0, 1)] + [(f"{dt}_{dn}", db, dd, 0)
 
 DTYPES = ("f32", "f64", "bf16")
 OPS = ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd")
-FUSED_OPS = ("box_grid_attn_fwd", "box_grid_attn_bwd")
+FUSED_OPS = ("box_grid_attn_fwd", "box_grid_attn_bwd", "box_grid_softmax_attn_fwd", "box_grid_softmax_attn_bwd")
 EXPORTS = (
     ["bxr_abi_version", "bxr_status_string", "bxr_last_error_detail", "bxr_last_launch_count",
      "bxr_attn_bwd_workspace_bytes", "bxr_box_grid_attn_workspace_bytes"]
@@ -119,6 +119,10 @@ def _declare(lib):
         f = getattr(lib, f"bxr_box_grid_attn_fwd_{dt}")
         f.restype, f.argtypes = i, [vp] * 8 + dims + [vp] + [vp, sz, u, vp]
         f = getattr(lib, f"bxr_box_grid_attn_bwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 9 + dims + [vp] * 4 + [vp, sz, u, vp]
+        f = getattr(lib, f"bxr_box_grid_softmax_attn_fwd_{dt}")
+        f.restype, f.argtypes = i, [vp] * 8 + dims + [vp, vp] + [vp, sz, u, vp]
+        f = getattr(lib, f"bxr_box_grid_softmax_attn_bwd_{dt}")
         f.restype, f.argtypes = i, [vp] * 9 + dims + [vp] * 4 + [vp, sz, u, vp]
     lib.bxr_box_grid_attn_workspace_bytes.restype = c.c_size_t
     lib.bxr_box_grid_attn_workspace_bytes.argtypes = [c.c_int] * 9 + [c.c_uint]

@@ -29,10 +29,21 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .box_attention_func import (BoxAttnBf16Function, BoxAttnFunction, BoxGridAttnBf16Function, BoxGridAttnFunction,
+                                 BoxGridSoftmaxAttnBf16Function, BoxGridSoftmaxAttnFunction,
                                  InstanceAttnBf16Function, InstanceAttnFunction)
 
 _AMP_NATIVE = False
 _FUSED_GRID = False
+_FUSED_SOFTMAX = False
+
+
+def set_fused_softmax(flag: bool):
+    """With ``set_fused_grid(True)``: ``BoxAttention`` / ``Box3dAttention`` also hand the attention LOGITS to the
+    op, which takes the softmax over a row's L*P points in its prologue and chains its gradient in its backward
+    (SURVEY.md 8 row f2).  The modules still return the attention weights (written by the kernel); they are
+    not differentiable through the module in this mode (BoxeR's callers discard them, box_transformer.py:346-354)."""
+    global _FUSED_SOFTMAX
+    _FUSED_SOFTMAX = bool(flag)
 
 
 def set_fused_grid(flag: bool):
@@ -63,6 +74,11 @@ def _box_attn(value, v_shape, v_start_index, grid, weights, im2col_step):
 def _box_grid_attn(value, v_shape, v_start_index, boxes, angles, valid_ratios, kernel_indices, weights, im2col_step):
     fn = BoxGridAttnBf16Function if _use_bf16(value) else BoxGridAttnFunction
     return fn.apply(value, v_shape, v_start_index, boxes, angles, valid_ratios, kernel_indices, weights, im2col_step)
+
+
+def _box_grid_softmax_attn(value, v_shape, v_start_index, boxes, angles, valid_ratios, kernel_indices, logits, im2col_step):
+    fn = BoxGridSoftmaxAttnBf16Function if _use_bf16(value) else BoxGridSoftmaxAttnFunction
+    return fn.apply(value, v_shape, v_start_index, boxes, angles, valid_ratios, kernel_indices, logits, im2col_step)
 
 
 def _instance_attn(value, v_shape, v_start_index, grid, sw, lw, k, im2col_step):
@@ -159,6 +175,21 @@ class _BoxAttentionBase(nn.Module):
         sampled_grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
         return _box_attn(value, v_shape, v_start_index, sampled_grid, weights, self.im2col_step)
 
+    def _attend_logits(self, query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, logits):
+        """softmax over (L, K, K) + box attention; returns (output, attention weights (B,Nq,H,L,K,K))."""
+        b, l1 = query.shape[:2]
+        shape6 = (b, l1, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
+        if _FUSED_GRID and _FUSED_SOFTMAX and value.is_cuda:
+            boxes, angles = self._boxes_and_angles(query, ref_windows)
+            vr = None
+            if v_valid_ratios is not None:
+                vr = v_valid_ratios.reshape(v_valid_ratios.shape[0], self.num_level, 2)
+            out, attn = _box_grid_softmax_attn(value, v_shape, v_start_index, boxes, angles, vr, self.kernel_indices,
+                                               logits.view(shape6), self.im2col_step)
+            return out, attn.view(shape6)
+        attn = F.softmax(logits.view(b, l1, self.num_head, -1), dim=-1).view(shape6)
+        return self._attend(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, attn), attn
+
     def _project_value(self, value, v_mask):
         b, l2 = value.shape[:2]
         value = self.value_proj(value)
@@ -176,10 +207,8 @@ class BoxAttention(_BoxAttentionBase):
     def forward(self, query, value, v_shape, v_mask, v_start_index, v_valid_ratios, ref_windows):
         b, l1 = query.shape[:2]
         value = self._project_value(value, v_mask)
-        attn_weights = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
-        attn_weights = F.softmax(attn_weights.view(b, l1, self.num_head, -1), dim=-1)
-        attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
-        output = self._attend(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, attn_weights)
+        logits = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
+        output, attn_weights = self._attend_logits(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, logits)
         output = self.out_proj(output)
         return output, attn_weights
 
@@ -280,9 +309,7 @@ class Box3dAttention(_BoxAttentionBase):
     def forward(self, query, value, v_shape, v_mask, v_start_index, v_valid_ratios, ref_windows):
         b, l1 = query.shape[:2]
         value = self._project_value(value, v_mask)
-        attn_weights = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
-        attn_weights = F.softmax(attn_weights.view(b, l1, self.num_head, -1), dim=-1)
-        attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
-        output = self._attend(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, attn_weights)
+        logits = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
+        output, attn_weights = self._attend_logits(query, value, v_shape, v_start_index, v_valid_ratios, ref_windows, logits)
         output = self.out_proj(output)
         return output, attn_weights

@@ -114,6 +114,42 @@ class BoxGridAttnFunction(Function):
         return gv, None, None, gb, ga, None, None, gw, None
 
 
+class BoxGridSoftmaxAttnFunction(Function):
+    """Fused softmax -> box -> grid -> attention: as ``BoxGridAttnFunction`` but takes the
+    attention LOGITS (B,Nq,H,L*P or B,Nq,H,L,K,K) the modules feed to ``F.softmax(dim=-1)``
+    (box_attention.py:227-231) and returns ``(output, attention_weights)``; ``attention_weights`` (what the module
+    returns to its caller) is a by-product and not differentiable through this Function."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, shapes, lsi, boxes, angles, valid_ratios, kernel_indices, logits, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.has = (angles is not None, valid_ratios is not None)
+        boxes = boxes.contiguous()
+        angles_c = angles.contiguous() if angles is not None else None
+        vr = valid_ratios.contiguous() if valid_ratios is not None else None
+        kidx = kernel_indices.to(boxes.dtype).contiguous()
+        out, attn = ops.box_grid_attn_forward(value, shapes, lsi, boxes, angles_c, vr, kidx, logits.contiguous(),
+                                              im2col_step, softmax=True)
+        ctx.save_for_backward(*([value, shapes, lsi, boxes, kidx, attn] + [t for t in (angles_c, vr) if t is not None]))
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, grad_output, _grad_attn):
+        if not grad_output.is_contiguous():
+            grad_output = grad_output.contiguous()
+        value, shapes, lsi, boxes, kidx, attn = ctx.saved_tensors[:6]
+        rest = list(ctx.saved_tensors[6:])
+        angles = rest.pop(0) if ctx.has[0] else None
+        vr = rest.pop(0) if ctx.has[1] else None
+        gv, gb, ga, gz = ops.box_grid_attn_backward(value, shapes, lsi, boxes, angles, vr, kidx, attn,
+                                                    grad_output.to(value.dtype), ctx.im2col_step, softmax=True)
+        return gv, None, None, gb, ga, None, None, gz, None
+
+
 # --------------------------------------------------------------------------- bf16 opt-in
 def _bf16_inputs(value, loc, *weights):
     return (value.to(torch.bfloat16).contiguous(), loc.float().contiguous(),
@@ -167,6 +203,41 @@ class InstanceAttnBf16Function(Function):
                 grad_mask_output.to(torch.bfloat16).contiguous(), ctx.im2col_step)
         dv, dl, ds, dw = ctx.in_dtypes
         return gv.to(dv), None, None, gl.to(dl), gs.to(ds), gw.to(dw), None, None
+
+
+class BoxGridSoftmaxAttnBf16Function(Function):
+    """bf16 value / output variant of BoxGridSoftmaxAttnFunction (boxes, angles, logits fp32)."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, lsi, boxes, angles, valid_ratios, kernel_indices, logits, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.has = (angles is not None, valid_ratios is not None)
+        ctx.in_dtypes = (value.dtype, boxes.dtype, angles.dtype if angles is not None else None, logits.dtype)
+        with torch.autocast("cuda", enabled=False):
+            v = value.to(torch.bfloat16).contiguous()
+            bx = boxes.float().contiguous()
+            an = angles.float().contiguous() if angles is not None else None
+            vr = valid_ratios.float().contiguous() if valid_ratios is not None else None
+            kidx = kernel_indices.float().contiguous()
+            out, attn = ops.box_grid_attn_forward(v, shapes, lsi, bx, an, vr, kidx, logits.float().contiguous(),
+                                                  im2col_step, softmax=True)
+        ctx.save_for_backward(*([v, shapes, lsi, bx, kidx, attn] + [t for t in (an, vr) if t is not None]))
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output, _grad_attn):
+        v, shapes, lsi, bx, kidx, a = ctx.saved_tensors[:6]
+        rest = list(ctx.saved_tensors[6:])
+        an = rest.pop(0) if ctx.has[0] else None
+        vr = rest.pop(0) if ctx.has[1] else None
+        with torch.autocast("cuda", enabled=False):
+            gv, gb, ga, gz = ops.box_grid_attn_backward(v, shapes, lsi, bx, an, vr, kidx, a,
+                                                        grad_output.to(torch.bfloat16).contiguous(), ctx.im2col_step,
+                                                        softmax=True)
+        dv, db, da, dz = ctx.in_dtypes
+        return (gv.to(dv), None, None, gb.to(db), ga.to(da) if ga is not None else None, None, None, gz.to(dz), None)
 
 
 class BoxGridAttnBf16Function(Function):

@@ -210,15 +210,15 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
     return p.rows >= 2LL * sm_count() * groups;     // small (decoder-sized) calls keep the point-split kernels
 }
 
-template <typename TV, int G, int SUB, int PPL, bool FUSED>
+template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX>
 int fwd_win(AttnParams& p, cudaStream_t st) {
     p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED>>(p, st, "box_fwd_win_kernel");
+    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED, SMAX>>(p, st, "box_fwd_win_kernel");
 }
-template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED>
+template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX>
 int bwd_win(AttnParams& p, cudaStream_t st) {
     p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED>>(p, st, "box_bwd_win_kernel");
+    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED, SMAX>>(p, st, "box_bwd_win_kernel");
 }
 
 // (G, SUB, PPL): SUB lanes share a level's points, PPL points per lane; P <= SUB * PPL.
@@ -243,13 +243,13 @@ int win_key(int P, int g) {
     return g * 1000 + sub * 10 + ppl;
 }
 
-template <typename TV, bool FUSED = false>
+template <typename TV, bool FUSED = false, bool SMAX = false>
 int dispatch_fwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_win<TV, G, SUB, PPL, FUSED>(p, st)))
+    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_win<TV, G, SUB, PPL, FUSED, SMAX>(p, st)))
 }
-template <typename TV, typename ACC, bool FUSED = false>
+template <typename TV, typename ACC, bool FUSED = false, bool SMAX = false>
 int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC, FUSED>(p, st)))
+    BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC, FUSED, SMAX>(p, st)))
 }
 
 // ---- staged-row kernels (boxattn_staged.cuh): the window algorithm with TMA-staged row operands.
@@ -443,6 +443,7 @@ struct FusedArgs {
     const void* kidx = nullptr;
     void* grad_boxes = nullptr;
     void* grad_angles = nullptr;
+    bool softmax = false;     // grad_w0 receives the gradient of the logits (softmax chained in-kernel)
 };
 
 template <typename TV, typename TW, bool INSTANCE>
@@ -537,12 +538,14 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
         }
         if (win && g8) {
             if constexpr (!INSTANCE) {
-                if (fused) status = det ? dispatch_bwd_win<bf16x4_t, long long, true>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float, true>(g8, p, st);
+                if (fused && fused->softmax) status = det ? dispatch_bwd_win<bf16x4_t, long long, true, true>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float, true, true>(g8, p, st);
+                else if (fused) status = det ? dispatch_bwd_win<bf16x4_t, long long, true>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float, true>(g8, p, st);
                 else status = det ? dispatch_bwd_win<bf16x4_t, long long>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float>(g8, p, st);
             }
         } else if (win) {
             if constexpr (!INSTANCE) {
-                if (fused) status = det ? dispatch_bwd_win<TV, long long, true>(g, p, st) : dispatch_bwd_win<TV, float, true>(g, p, st);
+                if (fused && fused->softmax) status = det ? dispatch_bwd_win<TV, long long, true, true>(g, p, st) : dispatch_bwd_win<TV, float, true, true>(g, p, st);
+                else if (fused) status = det ? dispatch_bwd_win<TV, long long, true>(g, p, st) : dispatch_bwd_win<TV, float, true>(g, p, st);
                 else status = det ? dispatch_bwd_win<TV, long long>(g, p, st) : dispatch_bwd_win<TV, float>(g, p, st);
             }
         } else if (own) {
@@ -594,6 +597,30 @@ int launch_grid_bwd(const AttnParams& p, const TW* grad_loc, cudaStream_t st) {
     return BXR_OK;
 }
 
+template <typename TW>
+int launch_softmax_rows(const TW* logits, TW* out, long long rows, int n, cudaStream_t st) {
+    if (rows <= 0 || n <= 0) return BXR_OK;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    softmax_rows_kernel<TW><<<(int)blocks, 256, 0, st>>>(logits, out, rows, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "softmax_rows_kernel");
+    ++g_launches;
+    return BXR_OK;
+}
+
+template <typename TW>
+int launch_softmax_bwd_rows(const TW* w, TW* g, long long rows, int n, cudaStream_t st) {
+    if (rows <= 0 || n <= 0) return BXR_OK;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    softmax_bwd_rows_kernel<TW><<<(int)blocks, 256, 0, st>>>(w, g, rows, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "softmax_bwd_rows_kernel");
+    ++g_launches;
+    return BXR_OK;
+}
+
 size_t fused_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H, int D, int L, int Nq, int P, unsigned flags) {
     if (B < 0 || S < 0 || H < 0 || D < 0 || L < 0 || Nq < 0 || P < 0) return 0;
     const size_t tw = dtype_bytes == 8 ? 8 : 4;
@@ -608,7 +635,8 @@ size_t fused_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H,
 template <typename TV, typename TW>
 int fused_forward(const TV* value, const int64_t* shapes, const int64_t* level_start, const TW* boxes, const TW* angles,
                   const TW* valid_ratios, const TW* kidx, const TW* attn, int B, int S, int H, int D, int L, int Nq, int P,
-                  TV* out, void* ws, size_t ws_bytes, unsigned flags, bxr_stream_t stream) {
+                  TV* out, void* ws, size_t ws_bytes, unsigned flags, bxr_stream_t stream, TW* attn_out = nullptr) {
+    // attn_out != NULL: `attn` holds logits; their softmax over (L, P) is written to attn_out and used as the weights
     g_launches = 0;
     g_detail[0] = 0;
     if (int s = check_dims(B, S, H, D, L, Nq, P)) return s;
@@ -616,17 +644,37 @@ int fused_forward(const TV* value, const int64_t* shapes, const int64_t* level_s
     memset(&p, 0, sizeof(p));
     fill_sizes(p, B, S, H, D, L, Nq, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p.rows == 0 || D == 0) return BXR_OK;
-    if (!out) return fail(BXR_ERR_NULL_POINTER, "output pointer is NULL");
-    if (p.LP == 0 || S == 0) {
+    if (p.rows == 0) return BXR_OK;
+    if (D == 0 || S == 0 || p.LP == 0) {    // nothing to sample: zero output, but the weights are still defined
+        if (attn_out && p.LP > 0) {
+            if (!attn) return fail(BXR_ERR_NULL_POINTER, "input pointer is NULL");
+            if (int s = launch_softmax_rows<TW>(attn, attn_out, p.rows, p.LP, st)) return s;
+        }
+        if (D == 0) return BXR_OK;
+        if (!out) return fail(BXR_ERR_NULL_POINTER, "output pointer is NULL");
         BXR_CUDA(cudaMemsetAsync(out, 0, sizeof(TV) * (size_t)p.rows * D, st));
         return BXR_OK;
     }
+    if (!out) return fail(BXR_ERR_NULL_POINTER, "output pointer is NULL");
     if (!value || !shapes || !level_start || !boxes || !kidx || !attn) return fail(BXR_ERR_NULL_POINTER, "input pointer is NULL");
     p.value = value; p.shapes = shapes; p.level_start = level_start; p.w0 = attn; p.out = out;
-    p.boxes = boxes; p.angles = angles; p.valid_ratios = valid_ratios; p.kidx = kidx;
+    p.boxes = boxes; p.angles = angles; p.valid_ratios = valid_ratios; p.kidx = kidx; p.attn_out = attn_out;
 
     const bool aligned = aligned16(value) && aligned16(out) && aligned16(boxes) && aligned8(kidx) && (!valid_ratios || aligned8(valid_ratios));
+    if constexpr (!std::is_same<TV, double>::value) {
+        if (attn_out && aligned && fused_applies((int)sizeof(TV), B, S, H, D, L, P, flags)) {
+            if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
+                if (const int g8 = bf16_lane8_group(D)) return dispatch_fwd_win<bf16x4_t, true, true>(g8, p, st);
+            }
+            return dispatch_fwd_win<TV, true, true>(vec_group<TV>(D, p.LP), p, st);
+        }
+    }
+    if (attn_out) {     // general path: softmax first, then as with given weights
+        if (int s = launch_softmax_rows<TW>(attn, attn_out, p.rows, p.LP, st)) return s;
+        attn = attn_out;
+        p.w0 = attn_out;
+        p.attn_out = nullptr;
+    }
     if constexpr (!std::is_same<TV, double>::value) {
         if (aligned && fused_applies((int)sizeof(TV), B, S, H, D, L, P, flags)) {
             if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
@@ -654,7 +702,8 @@ template <typename TV, typename TW>
 int fused_backward(const TV* value, const int64_t* shapes, const int64_t* level_start, const TW* boxes, const TW* angles,
                    const TW* valid_ratios, const TW* kidx, const TW* attn, const TV* grad_out,
                    int B, int S, int H, int D, int L, int Nq, int P, TV* grad_value, TW* grad_boxes, TW* grad_angles,
-                   TW* grad_attn, void* ws, size_t ws_bytes, unsigned flags, bxr_stream_t stream) {
+                   TW* grad_attn, void* ws, size_t ws_bytes, unsigned flags, bxr_stream_t stream, bool smax = false) {
+    // smax: `attn` are the softmax weights the forward wrote; grad_attn receives the gradient of the LOGITS
     g_detail[0] = 0;
     if (int s = check_dims(B, S, H, D, L, Nq, P)) return s;
     const long long rows = (long long)B * Nq * H;
@@ -663,6 +712,7 @@ int fused_backward(const TV* value, const int64_t* shapes, const int64_t* level_
     FusedArgs fa;
     fa.boxes = boxes; fa.angles = angles; fa.valid_ratios = valid_ratios; fa.kidx = kidx;
     fa.grad_boxes = grad_boxes; fa.grad_angles = angles ? grad_angles : nullptr;
+    fa.softmax = smax;
     const size_t bwd_ws = align256(workspace_bytes((int)sizeof(TV), (long long)B * S * H * D, flags));
     if (bwd_ws && (!ws || ws_bytes < bwd_ws)) return fail(BXR_ERR_WORKSPACE, "workspace too small");
 
@@ -705,6 +755,10 @@ int fused_backward(const TV* value, const int64_t* shapes, const int64_t* level_
     } else if (p.rows > 0 && p.L > 0) {
         BXR_CUDA(cudaMemsetAsync(grad_boxes, 0, sizeof(TW) * (size_t)p.rows * p.L * 4, st));
         if (fa.grad_angles) BXR_CUDA(cudaMemsetAsync(fa.grad_angles, 0, sizeof(TW) * (size_t)p.rows * p.L, st));
+    }
+    if (smax && p.rows > 0 && p.LP > 0) {
+        if (int s = launch_softmax_bwd_rows<TW>(attn, grad_attn, p.rows, p.LP, st)) return s;
+        extra += 1;
     }
     g_launches = extra;
     return BXR_OK;
@@ -769,6 +823,31 @@ size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, i
                                      workspace, workspace_bytes, flags, stream);                                     \
     }
 
+#define BXR_DEFINE_SMAX_FWD(SUF, TVABI, TV, TW)                                                                      \
+    int bxr_box_grid_softmax_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,   \
+                                            const TW* boxes, const TW* angles, const TW* valid_ratios,               \
+                                            const TW* kidx, const TW* logits, int B, int S, int H, int D, int L,     \
+                                            int Nq, int P, TVABI* out, TW* attn_out, void* workspace,                \
+                                            size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {           \
+        if (!attn_out && (long long)B * Nq * H * L * P > 0) return fail(BXR_ERR_NULL_POINTER, "attn_out is NULL");   \
+        return fused_forward<TV, TW>(reinterpret_cast<const TV*>(value), shapes, level_start, boxes, angles,         \
+                                     valid_ratios, kidx, logits, B, S, H, D, L, Nq, P, reinterpret_cast<TV*>(out),   \
+                                     workspace, workspace_bytes, flags, stream, attn_out);                           \
+    }
+
+#define BXR_DEFINE_SMAX_BWD(SUF, TVABI, TV, TW)                                                                      \
+    int bxr_box_grid_softmax_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,   \
+                                            const TW* boxes, const TW* angles, const TW* valid_ratios,               \
+                                            const TW* kidx, const TW* attn, const TVABI* grad_out, int B, int S,     \
+                                            int H, int D, int L, int Nq, int P, TVABI* grad_value, TW* grad_boxes,   \
+                                            TW* grad_angles, TW* grad_logits, void* workspace,                       \
+                                            size_t workspace_bytes, unsigned flags, bxr_stream_t stream) {           \
+        return fused_backward<TV, TW>(reinterpret_cast<const TV*>(value), shapes, level_start, boxes, angles,        \
+                                      valid_ratios, kidx, attn, reinterpret_cast<const TV*>(grad_out), B, S, H, D,   \
+                                      L, Nq, P, reinterpret_cast<TV*>(grad_value), grad_boxes, grad_angles,          \
+                                      grad_logits, workspace, workspace_bytes, flags, stream, true);                 \
+    }
+
 #define BXR_DEFINE_OPS_BWD(SUF, TVABI, TV, TW)                                                                       \
     int bxr_box_attn_bwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start, const TW* loc, \
                                const TW* attn, const TVABI* grad_out, int B, int S, int H, int D, int L, int Nq,     \
@@ -803,12 +882,12 @@ size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, i
     }
 
 #if BXR_TU_DIRS & 1
-#define BXR_FWD(...) BXR_DEFINE_OPS_FWD(__VA_ARGS__)
+#define BXR_FWD(...) BXR_DEFINE_OPS_FWD(__VA_ARGS__) BXR_DEFINE_SMAX_FWD(__VA_ARGS__)
 #else
 #define BXR_FWD(...)
 #endif
 #if BXR_TU_DIRS & 2
-#define BXR_BWD(...) BXR_DEFINE_OPS_BWD(__VA_ARGS__)
+#define BXR_BWD(...) BXR_DEFINE_OPS_BWD(__VA_ARGS__) BXR_DEFINE_SMAX_BWD(__VA_ARGS__)
 #else
 #define BXR_BWD(...)
 #endif

@@ -79,4 +79,44 @@ __global__ void grid_bwd_kernel(const AttnParams p, const TW* __restrict__ grad_
     }
 }
 
+// ---- softmax over the last dimension (n = L*P) of (rows, n), one warp per row: the general-path companions
+// of the in-kernel softmax of the window kernels
+template <typename TW>
+__global__ void softmax_rows_kernel(const TW* __restrict__ logits, TW* __restrict__ out, long long rows, int n) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const TW* z = logits + r * n;
+        TW mx = -INFINITY;
+        for (int i = lane; i < n; i += 32) mx = z[i] > mx ? z[i] : mx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const TW t = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = t > mx ? t : mx;
+        }
+        TW sum = 0;
+        for (int i = lane; i < n; i += 32) sum += exp(z[i] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const TW inv = (TW)1 / sum;
+        for (int i = lane; i < n; i += 32) out[r * n + i] = exp(z[i] - mx) * inv;
+    }
+}
+
+// g <- w * (g - sum_row(w * g)), in place
+template <typename TW>
+__global__ void softmax_bwd_rows_kernel(const TW* __restrict__ w, TW* __restrict__ g, long long rows, int n) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < rows; r += nwarps) {
+        TW dotp = 0;
+        for (int i = lane; i < n; i += 32) dotp += w[r * n + i] * g[r * n + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dotp += __shfl_xor_sync(0xffffffffu, dotp, o);
+        for (int i = lane; i < n; i += 32) g[r * n + i] = w[r * n + i] * (g[r * n + i] - dotp);
+    }
+}
+
 }  // namespace bxr

@@ -57,6 +57,7 @@ struct AttnParams {
     const void* kidx;             // (P,2)        TW  kernel_indices
     void* grad_boxes;             // (B,Nq,H,L,4) TW
     void* grad_angles;            // (B,Nq,H,L)   TW  or nullptr
+    void* attn_out;               // (B,Nq,H,L,P) TW  softmax weights written by the fused-softmax forward
     // sizes
     int B, S, H, D, L, Nq, P;
     int LP;                       // L*P

@@ -149,14 +149,38 @@ __device__ __forceinline__ void box_point(const LevelBox& q, float kx, float ky,
     y = (q.cy + (ux * q.sn + uy * q.cs)) * q.vy;
 }
 
+// softmax over a row's L*P logits, fused into the op (box_attention.py:227-231):
+// weight = exp(logit - row max) / row sum
+struct RowSoftmax {
+    float mx, inv;
+};
+template <int G>
+__device__ __forceinline__ RowSoftmax row_softmax(const float* __restrict__ logits, int LP, int lane, unsigned gm) {
+    float mx = -INFINITY;
+    for (int i = lane; i < LP; i += G) mx = fmaxf(mx, __ldg(logits + i));
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gm, mx, o));
+    float sum = 0.f;
+    for (int i = lane; i < LP; i += G) sum += expf(__ldg(logits + i) - mx);
+    sum = gsum<G>(sum, gm);
+    RowSoftmax r;
+    r.mx = mx;
+    r.inv = 1.f / sum;
+    return r;
+}
+
+template <bool SMAX>
 __device__ __forceinline__ LanePoint lane_point_box(const LevelBox& q, const float* __restrict__ kidx,
-                                                    const float* __restrict__ w_l, int pt, int P, int h, int w) {
+                                                    const float* __restrict__ w_l, int pt, int P, int h, int w,
+                                                    const RowSoftmax& sm) {
     const bool act = pt < P;
     const int pc = act ? pt : 0;
     const float2 k = __ldg(reinterpret_cast<const float2*>(kidx) + pc);
     float x, y;
     box_point(q, k.x, k.y, x, y);
-    return lane_point_xy(x, y, __ldg(w_l + pc), act, h, w);
+    float aw = __ldg(w_l + pc);
+    if (SMAX) aw = expf(aw - sm.mx) * sm.inv;
+    return lane_point_xy(x, y, aw, act, h, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,8 +223,10 @@ struct SubWin {
 
 // ------------------------------------------------------------------------------------------------
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
-template <typename TV, int G, int SUB, int PPL, bool FUSED>
+// SMAX (with FUSED): `w0` holds logits; the softmax over the row's L*P points is taken here and written to attn_out.
+template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX = false>
 __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_MINB) box_fwd_win_kernel(const AttnParams p) {
+    static_assert(FUSED || !SMAX, "the softmax prologue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
@@ -232,6 +258,9 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
         const unsigned vrow = (unsigned)(b * p.S * HDV + head * G + lane);
         const float* loc_row = FUSED ? nullptr : loc + row * p.LP * 2;
         const float* w_row = w0 + row * p.LP;
+        RowSoftmax rsm;
+        rsm.mx = 0.f; rsm.inv = 1.f;
+        if constexpr (SMAX) rsm = row_softmax<G>(w_row, p.LP, lane, gm);
 
         float acc[VEC];
 #pragma unroll
@@ -251,8 +280,11 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
                 const int ptn = lact ? slane + k * SUB : p.P;
-                if constexpr (FUSED) pt[k] = lane_point_box(lbx, static_cast<const float*>(p.kidx), w_row + lmc * p.P, ptn, p.P, mh, mw);
+                if constexpr (FUSED) pt[k] = lane_point_box<SMAX>(lbx, static_cast<const float*>(p.kidx), w_row + lmc * p.P, ptn, p.P, mh, mw, rsm);
                 else pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, ptn, p.P, mh, mw);
+                if constexpr (SMAX) {
+                    if (ptn < p.P) static_cast<float*>(p.attn_out)[row * p.LP + lmc * p.P + ptn] = pt[k].aw;
+                }
                 if (pt[k].inside) {
                     bx0 = min(bx0, pt[k].x0); bx1 = max(bx1, pt[k].x0 + 1);
                     by0 = min(by0, pt[k].y0); by1 = max(by1, pt[k].y0 + 1);
@@ -420,8 +452,11 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
     return (hi ? 2 : 0) + (lo ? 1 : 0);
 }
 
-template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED>
+// SMAX (with FUSED): `w0` holds the softmax weights the forward wrote; the weight gradients are chained through
+// the softmax before they leave the kernel:  grad_logit = w * (grad_w - sum_row(w * grad_w)).
+template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX = false>
 __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_MINB) box_bwd_win_kernel(const AttnParams p) {
+    static_assert(FUSED || !SMAX, "the softmax epilogue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
@@ -476,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
                 const int ptn = lact ? slane + k * SUB : p.P;
-                if constexpr (FUSED) pt[k] = lane_point_box(lbx, static_cast<const float*>(p.kidx), w_row + lmc * p.P, ptn, p.P, mh, mw);
+                if constexpr (FUSED) pt[k] = lane_point_box<false>(lbx, static_cast<const float*>(p.kidx), w_row + lmc * p.P, ptn, p.P, mh, mw, RowSoftmax{0.f, 1.f});
                 else pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, ptn, p.P, mh, mw);
                 g_a[k] = g_x[k] = g_y[k] = 0.f;
                 if (pt[k].inside) {
@@ -686,6 +721,16 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
                     if (p.grad_angles) static_cast<float*>(p.grad_angles)[rl] = ba;
                 }
             }
+        }
+        if constexpr (SMAX) {
+            // the row's weight gradients were written by the lanes of this group: read them back (L2) after a
+            // group barrier and chain them through the softmax, in place
+            __syncwarp(gm);
+            float* gw = grad_w0 + row * p.LP;
+            float dotp = 0.f;
+            for (int i = lane; i < p.LP; i += G) dotp += __ldg(w_row + i) * __ldcg(gw + i);
+            dotp = gsum<G>(dotp, gm);
+            for (int i = lane; i < p.LP; i += G) gw[i] = __ldg(w_row + i) * (__ldcg(gw + i) - dotp);
         }
     }
 }

@@ -297,9 +297,12 @@ def _aligned16(t):
 
 
 def box_grid_attn_forward(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios, kernel_indices,
-                          attn_weight, im2col_step=64):
+                          attn_weight, im2col_step=64, softmax=False):
     """out = box_attn_forward(value, ..., grid(boxes, angles, valid_ratios, kernel_indices), attn_weight) with the
-    K x K grid of BoxAttention._where_to_attend (box_attention.py:196-214; rotated: :304-338) generated in-kernel."""
+    K x K grid of BoxAttention._where_to_attend (box_attention.py:196-214; rotated: :304-338) generated in-kernel.
+
+    softmax=True: ``attn_weight`` holds the attention LOGITS; their softmax over a row's L*P
+    points (box_attention.py:227-231) is taken in the kernel and returned too -> ``(out, attention_weights)``."""
     B, S, H, D, L, Nq, P = _fused_geometry(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios,
                                            kernel_indices, attn_weight)
     opt = tuple(t for t in (angles, valid_ratios) if t is not None)
@@ -308,22 +311,28 @@ def box_grid_attn_forward(value, spatial_shapes, level_start_index, boxes, angle
     lib = _native.load()
     value, boxes = _aligned16(value), _aligned16(boxes)
     out = torch.empty((B, Nq, H * D), dtype=value.dtype, device=value.device)
+    attn_out = torch.empty_like(attn_weight) if softmax else None
     with _on_device(value.device):
         n = lib.bxr_box_grid_attn_workspace_bytes(value.element_size(), 0, B, S, H, D, L, Nq, P, _PATH_FLAGS)
         ws = torch.empty(n, dtype=torch.uint8, device=value.device) if n else None
-        st = _fn(f"bxr_box_grid_attn_fwd_{suf}")(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), boxes.data_ptr(),
-            angles.data_ptr() if angles is not None else None,
-            valid_ratios.data_ptr() if valid_ratios is not None else None,
-            kernel_indices.data_ptr(), attn_weight.data_ptr(), B, S, H, D, L, Nq, P, out.data_ptr(),
-            ws.data_ptr() if ws is not None else None, n, _PATH_FLAGS, _stream(value.device))
+        head = (value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), boxes.data_ptr(),
+                angles.data_ptr() if angles is not None else None,
+                valid_ratios.data_ptr() if valid_ratios is not None else None,
+                kernel_indices.data_ptr(), attn_weight.data_ptr(), B, S, H, D, L, Nq, P, out.data_ptr())
+        tail = (ws.data_ptr() if ws is not None else None, n, _PATH_FLAGS, _stream(value.device))
+        if softmax:
+            st = _fn(f"bxr_box_grid_softmax_attn_fwd_{suf}")(*head, attn_out.data_ptr(), *tail)
+        else:
+            st = _fn(f"bxr_box_grid_attn_fwd_{suf}")(*head, *tail)
     _native.check(st, "box_grid_attn_forward")
-    return out
+    return (out, attn_out) if softmax else out
 
 
 def box_grid_attn_backward(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios, kernel_indices,
-                           attn_weight, grad_output, im2col_step=64):
-    """-> [grad_value, grad_boxes, grad_angles | None, grad_attn_weight]"""
+                           attn_weight, grad_output, im2col_step=64, softmax=False):
+    """-> [grad_value, grad_boxes, grad_angles | None, grad_attn_weight]
+    softmax=True: ``attn_weight`` are the softmax weights the softmax forward returned; the last gradient is the
+    gradient of the LOGITS."""
     B, S, H, D, L, Nq, P = _fused_geometry(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios,
                                            kernel_indices, attn_weight)
     opt = tuple(t for t in (angles, valid_ratios) if t is not None)
@@ -342,7 +351,7 @@ def box_grid_attn_backward(value, spatial_shapes, level_start_index, boxes, angl
     with _on_device(value.device):
         n = lib.bxr_box_grid_attn_workspace_bytes(value.element_size(), 1, B, S, H, D, L, Nq, P, flags)
         ws = torch.empty(n, dtype=torch.uint8, device=value.device) if n else None
-        st = _fn(f"bxr_box_grid_attn_bwd_{suf}")(
+        st = _fn(f"bxr_box_grid_softmax_attn_bwd_{suf}" if softmax else f"bxr_box_grid_attn_bwd_{suf}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), boxes.data_ptr(),
             angles.data_ptr() if angles is not None else None,
             valid_ratios.data_ptr() if valid_ratios is not None else None,

@@ -152,6 +152,34 @@ BXR_DECLARE_FUSED(f32, float, float)
 BXR_DECLARE_FUSED(f64, double, double)
 BXR_DECLARE_FUSED(bf16, bxr_bf16, float)
 
+/*
+ * Fused softmax -> box -> grid -> attention.  As bxr_box_grid_attn_*, but takes the
+ * attention LOGITS (B, Nq, H, L*P) that BoxAttention.forward feeds to F.softmax(dim=-1)
+ * (e2edet/module/box_attention.py:227-231; Box3dAttention :348-352): the softmax over a (b, q, head) row's
+ * L*P points runs in the kernel prologue.
+ *   fwd: writes out and attn_out (B, Nq, H, L, P) = softmax(logits) -- the module returns it, the backward needs it.
+ *   bwd: takes attn (= the forward's attn_out) and returns grad_logits = attn * (grad_attn - sum_row(attn * grad_attn)).
+ * Workspace: bxr_box_grid_attn_workspace_bytes().
+ */
+#define BXR_DECLARE_SMAX(SUF, TV, TW)                                                                               \
+    int bxr_box_grid_softmax_attn_fwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,     \
+                                            const TW* boxes, const TW* angles, const TW* valid_ratios,              \
+                                            const TW* kernel_indices, const TW* logits,                             \
+                                            int B, int S, int H, int D, int L, int Nq, int P, TV* out, TW* attn_out, \
+                                            void* workspace, size_t workspace_bytes, unsigned flags,                \
+                                            bxr_stream_t stream);                                                   \
+    int bxr_box_grid_softmax_attn_bwd_##SUF(const TV* value, const int64_t* shapes, const int64_t* level_start,     \
+                                            const TW* boxes, const TW* angles, const TW* valid_ratios,              \
+                                            const TW* kernel_indices, const TW* attn, const TV* grad_out,           \
+                                            int B, int S, int H, int D, int L, int Nq, int P,                       \
+                                            TV* grad_value, TW* grad_boxes, TW* grad_angles, TW* grad_logits,       \
+                                            void* workspace, size_t workspace_bytes, unsigned flags,                \
+                                            bxr_stream_t stream);
+
+BXR_DECLARE_SMAX(f32, float, float)
+BXR_DECLARE_SMAX(f64, double, double)
+BXR_DECLARE_SMAX(bf16, bxr_bf16, float)
+
 #ifdef __cplusplus
 }
 #endif

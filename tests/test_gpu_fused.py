@@ -178,3 +178,100 @@ def test_modules_with_fused_grid_match_reference_modules(case, dtype, tol):
     assert len(flat) == int(gold["n_out"])
     for i, o in enumerate(flat):
         assert helpers.rel_err(o, gold[f"out{i}"]) <= tol, (case, i)
+
+
+# ================================================================== fused softmax
+def _ours_softmax(c, logits, dtype, deterministic=False):
+    import boxer_b200
+    tw = torch.float64 if dtype == torch.float64 else torch.float32
+    mv = lambda t, dt: None if t is None else t.to(DEV, dt).contiguous()
+    value = mv(c["value"], dtype).requires_grad_(True)
+    boxes = mv(c["boxes"], tw).requires_grad_(True)
+    angles = mv(c["angles"], tw)
+    if angles is not None:
+        angles.requires_grad_(True)
+    z = mv(logits, tw).requires_grad_(True)
+    boxer_b200.set_deterministic(deterministic)
+    try:
+        fn = boxer_b200.BoxGridSoftmaxAttnBf16Function if dtype == torch.bfloat16 else boxer_b200.BoxGridSoftmaxAttnFunction
+        out, attn = fn.apply(value, c["shapes"].to(DEV), c["start"].to(DEV), boxes, angles, mv(c["vr"], tw), mv(c["kidx"], tw), z, 64)
+        assert not attn.requires_grad
+        out.backward(mv(c["go"], out.dtype))
+    finally:
+        boxer_b200.set_deterministic(None)
+    return out.detach(), attn.detach(), (value.grad, boxes.grad, angles.grad if angles is not None else None, z.grad)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4), (torch.bfloat16, 1e-2)],
+                         ids=["f64", "f32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_fused_softmax_matches_reference_formulation(name, dtype, tol):
+    """logits -> F.softmax over (L,K,K) (box_attention.py:227-231) -> grid -> grid_sample oracle, autograd in fp64,
+    vs the op that takes the logits (in-kernel softmax where the window kernels apply, small kernels elsewhere)."""
+    from oracle import plain
+    c = _case(name)
+    g = torch.Generator().manual_seed(len(name))
+    B, Nq, H, L, K, _ = c["attn"].shape
+    logits = 2.0 * torch.randn(B, Nq, H, L, K, K, generator=g, dtype=torch.float64)
+    if dtype == torch.bfloat16:
+        c["value"] = c["value"].bfloat16().double()
+        c["go"] = c["go"].bfloat16().double()
+    # oracle
+    value = c["value"].clone().requires_grad_(True)
+    boxes = c["boxes"].clone().requires_grad_(True)
+    angles = c["angles"].clone().requires_grad_(True) if c["angles"] is not None else None
+    z = logits.clone().requires_grad_(True)
+    attn_ref = torch.softmax(z.view(B, Nq, H, -1), -1).view(B, Nq, H, L, K, K)
+    grid = plain.grid_from_boxes(boxes, angles, c["vr"], c["kidx"])
+    ref_out = plain.plain_box_attn(value.view(B, value.shape[1], -1), c["shapes"], 2 * grid - 1, attn_ref)
+    ref_out.backward(c["go"])
+
+    out, attn, gr = _ours_softmax(c, logits, dtype)
+    wtol = 1e-9 if dtype == torch.float64 else 2e-6
+    assert helpers.rel_err(attn, attn_ref.detach()) <= wtol, "attention weights"
+    assert helpers.rel_err(out, ref_out.detach()) <= tol, "out"
+    assert helpers.rel_err(gr[0], value.grad) <= tol, "grad_value"
+    assert helpers.rel_err(gr[3], z.grad) <= tol, "grad_logits"
+    if dtype == torch.float64:
+        assert helpers.rel_err(gr[1], boxes.grad) <= tol, "grad_boxes"
+        if angles is not None:
+            assert helpers.rel_err(gr[2], angles.grad) <= tol, "grad_angles"
+    # and deterministic mode chains the same softmax
+    if dtype == torch.float32:
+        d = _ours_softmax(c, logits, dtype, deterministic=True)
+        assert helpers.rel_err(d[2][3], z.grad) <= tol, "grad_logits (deterministic)"
+
+
+@pytest.mark.parametrize("case", ["box_3d_refs_masked", "box_4d_refs_k3", "box3d_rot", "box3d_norot_4d"])
+def test_modules_with_fused_softmax_match_reference_modules(case):
+    """BoxAttention / Box3dAttention with set_fused_grid + set_fused_softmax vs outputs of the reference's classes,
+    and the parameter gradients of that path vs the default (reference op-for-op) path on the same device."""
+    import boxer_b200
+    spec = refinputs.module_cases()[case]
+    gold = helpers.golden("modules_golden")[case]
+    mod = getattr(boxer_b200, spec["cls"])(**spec["ctor"]).double()
+    state = {k[len("param_"):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("param_")}
+    mod.load_state_dict(state, strict=True)
+    mod = mod.to(DEV, torch.float32)
+    args = [a.to(DEV, torch.float32) if (torch.is_tensor(a) and a.is_floating_point()) else (a.to(DEV) if torch.is_tensor(a) else a)
+            for a in refinputs.module_inputs(spec)]
+
+    def run(fused):
+        mod.zero_grad()
+        boxer_b200.set_fused_grid(fused)
+        boxer_b200.set_fused_softmax(fused)
+        try:
+            out, attn = mod(*args)
+            out.square().sum().backward()
+        finally:
+            boxer_b200.set_fused_grid(False)
+            boxer_b200.set_fused_softmax(False)
+        return out.detach(), attn.detach(), {n: p.grad.clone() for n, p in mod.named_parameters()}
+
+    out_f, attn_f, g_f = run(True)
+    out_d, attn_d, g_d = run(False)
+    assert helpers.rel_err(out_f, gold["out0"]) <= 1e-4
+    assert helpers.rel_err(attn_f, gold["out1"]) <= 1e-5
+    assert helpers.rel_err(out_f, out_d) <= 2e-5
+    for n in g_d:
+        assert helpers.rel_err(g_f[n], g_d[n]) <= 2e-4, n
