@@ -432,9 +432,29 @@ def variants(ops, dev, bw_peak):
         for fused in (False, True):
             boxer_b200.set_fused_grid(fused)
             r["fused_ms" if fused else "grid_ms"] = time_call(run_mod, reps=10)
+        boxer_b200.set_fused_softmax(True)          # + softmax in the op (row f2)
+        r["fused_softmax_ms"] = time_call(run_mod, reps=10)
+        boxer_b200.set_fused_softmax(False)
         boxer_b200.set_fused_grid(False)
         r["speedup"] = r["grid_ms"] / r["fused_ms"]
+        r["speedup_softmax"] = r["grid_ms"] / r["fused_softmax_ms"]
         res[f"module_BoxAttention_K{K}_fwdbwd"] = r
+        # op level: (softmax kernel + grid + loc-taking op) vs fused grid vs fused grid + softmax, fwd and bwd
+        with torch.no_grad():
+            boxes, _ = mod._boxes_and_angles(q, refw)
+            boxes = boxes.contiguous()
+            logits = torch.randn(1, S, 8, 4, K, K, device=dev)
+            attn = torch.softmax(logits.view(1, S, 8, -1), -1).view_as(logits)
+            kidx = mod.kernel_indices
+            v4 = w.value
+            go_m = torch.randn(1, S, 256, device=dev)
+            o = {}
+            o["fused_fwd_ms"] = time_call(lambda: ops.box_grid_attn_forward(v4, w.shapes, w.level_start, boxes, None, None, kidx, attn, 64))
+            o["fused_softmax_fwd_ms"] = time_call(lambda: ops.box_grid_attn_forward(v4, w.shapes, w.level_start, boxes, None, None, kidx, logits, 64, softmax=True))
+            o["fused_bwd_ms"] = time_call(lambda: ops.box_grid_attn_backward(v4, w.shapes, w.level_start, boxes, None, None, kidx, attn, go_m, 64))
+            o["fused_softmax_bwd_ms"] = time_call(lambda: ops.box_grid_attn_backward(v4, w.shapes, w.level_start, boxes, None, None, kidx, attn, go_m, 64, softmax=True))
+            o["torch_softmax_fwd_ms"] = time_call(lambda: torch.softmax(logits.view(1, S, 8, -1), -1))
+        res[f"op_box_grid_K{K}"] = o
 
     # warm vs L2-flushed: one launch at a time, a 512 MB write in between evicts value / loc from L2
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)

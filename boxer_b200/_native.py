@@ -41,6 +41,7 @@ EXPORTS = (
     ["bxr_abi_version", "bxr_status_string", "bxr_last_error_detail", "bxr_last_launch_count",
      "bxr_attn_bwd_workspace_bytes", "bxr_box_grid_attn_workspace_bytes"]
     + [f"bxr_{op}_{dt}" for op in OPS + FUSED_OPS for dt in DTYPES]
+    + [f"bxr_instance_weights_{d}_{dt}" for d in ("fwd", "bwd") for dt in ("f32", "f64")]
 )
 
 _lock = threading.Lock()
@@ -124,6 +125,11 @@ def _declare(lib):
         f.restype, f.argtypes = i, [vp] * 8 + dims + [vp, vp] + [vp, sz, u, vp]
         f = getattr(lib, f"bxr_box_grid_softmax_attn_bwd_{dt}")
         f.restype, f.argtypes = i, [vp] * 9 + dims + [vp] * 4 + [vp, sz, u, vp]
+    for dt in ("f32", "f64"):
+        f = getattr(lib, f"bxr_instance_weights_fwd_{dt}")
+        f.restype, f.argtypes = i, [vp, c.c_longlong, i, i, vp, vp, vp]
+        f = getattr(lib, f"bxr_instance_weights_bwd_{dt}")
+        f.restype, f.argtypes = i, [vp, vp, vp, c.c_longlong, i, i, vp, vp]
     lib.bxr_box_grid_attn_workspace_bytes.restype = c.c_size_t
     lib.bxr_box_grid_attn_workspace_bytes.argtypes = [c.c_int] * 9 + [c.c_uint]
     return lib

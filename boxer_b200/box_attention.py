@@ -30,7 +30,7 @@ import torch.nn.functional as F
 
 from .box_attention_func import (BoxAttnBf16Function, BoxAttnFunction, BoxGridAttnBf16Function, BoxGridAttnFunction,
                                  BoxGridSoftmaxAttnBf16Function, BoxGridSoftmaxAttnFunction,
-                                 InstanceAttnBf16Function, InstanceAttnFunction)
+                                 InstanceAttnBf16Function, InstanceAttnFunction, InstanceWeightsFunction)
 
 _AMP_NATIVE = False
 _FUSED_GRID = False
@@ -229,15 +229,19 @@ class InstanceAttention(_BoxAttentionBase):
         # a 2x2 logit map per (head, level), nearest-upsampled to KxK (box_attention.py:93-97)
         attn_weights = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
         attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, 2, 2)
-        attn_weights = attn_weights.repeat_interleave(k // 2, dim=-1).repeat_interleave(k // 2, dim=-2)
-
-        spatial_attn_weights = F.softmax(attn_weights.view(b, l1, self.num_head, -1), dim=-1)
-        spatial_attn_weights = spatial_attn_weights.view(b, l1, self.num_head, self.num_level, k, k)
+        fused_w = _FUSED_SOFTMAX and value.is_cuda and k % 2 == 0
+        if fused_w:     # both weight tensors from the 2x2 maps in one kernel
+            spatial_attn_weights, level_attn_weights = InstanceWeightsFunction.apply(attn_weights, k)
+        else:
+            attn_weights = attn_weights.repeat_interleave(k // 2, dim=-1).repeat_interleave(k // 2, dim=-2)
+            spatial_attn_weights = F.softmax(attn_weights.view(b, l1, self.num_head, -1), dim=-1)
+            spatial_attn_weights = spatial_attn_weights.view(b, l1, self.num_head, self.num_level, k, k)
 
         if not self.inferencing:
             sampled_grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
-            level_attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, k, k)
-            level_attn_weights = F.softmax(level_attn_weights, dim=3)
+            if not fused_w:
+                level_attn_weights = attn_weights.view(b, l1, self.num_head, self.num_level, k, k)
+                level_attn_weights = F.softmax(level_attn_weights, dim=3)
             output, mask_output = _instance_attn(value, v_shape, v_start_index, sampled_grid,
                                                  spatial_attn_weights, level_attn_weights, k, self.im2col_step)
             attn_weights = (spatial_attn_weights, level_attn_weights)

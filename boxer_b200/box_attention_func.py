@@ -150,6 +150,28 @@ class BoxGridSoftmaxAttnFunction(Function):
         return gv, None, None, gb, ga, None, None, gz, None
 
 
+class InstanceWeightsFunction(Function):
+    """``apply(logits (B,Nq,H,L,2,2), kernel_size) -> (spatial_w, level_w)``, each (B,Nq,H,L,K,K): InstanceAttention's
+    ``repeat_interleave`` x2 + softmax over (L,K,K) + softmax over L (box_attention.py:93-110) and their backward as
+    one kernel each way."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, logits, kernel_size):
+        logits = logits.contiguous()
+        ctx.kernel_size = int(kernel_size)
+        ctx.save_for_backward(logits)
+        return ops.instance_weights_forward(logits, kernel_size)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, grad_sw, grad_lw):
+        (logits,) = ctx.saved_tensors
+        return ops.instance_weights_backward(logits, grad_sw.to(logits.dtype).contiguous(),
+                                             grad_lw.to(logits.dtype).contiguous(), ctx.kernel_size), None
+
+
 # --------------------------------------------------------------------------- bf16 opt-in
 def _bf16_inputs(value, loc, *weights):
     return (value.to(torch.bfloat16).contiguous(), loc.float().contiguous(),

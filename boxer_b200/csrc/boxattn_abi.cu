@@ -823,6 +823,41 @@ size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, i
                                      workspace, workspace_bytes, flags, stream);                                     \
     }
 
+// InstanceAttention weights from the 2x2 logit maps (boxattn_fused.cuh); only float / double exist
+#define BXR_DEFINE_INSTW_FWD(SUF, T)                                                                                 \
+    int bxr_instance_weights_fwd_##SUF(const T* logits, long long rows, int L, int K, T* spatial_w, T* level_w,     \
+                                       bxr_stream_t stream) {                                                        \
+        g_launches = 0;                                                                                              \
+        g_detail[0] = 0;                                                                                             \
+        if (rows < 0 || L < 0 || K < 0 || L > BXR_MAX_LEVELS || (K & 1)) return fail(BXR_ERR_BAD_DIM, "rows, L >= 0, L <= 32, K even"); \
+        if (rows == 0 || L == 0 || K == 0) return BXR_OK;                                                            \
+        if (!logits || !spatial_w || !level_w) return fail(BXR_ERR_NULL_POINTER, "pointer is NULL");                 \
+        long long blocks = (rows + 7) / 8;                                                                           \
+        if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();                                                  \
+        inst_weights_fwd_kernel<T><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, spatial_w,    \
+                                                                                               level_w, rows, L, K); \
+        BXR_CUDA(cudaGetLastError());                                                                                \
+        ++g_launches;                                                                                                \
+        return BXR_OK;                                                                                               \
+    }
+#define BXR_DEFINE_INSTW_BWD(SUF, T)                                                                                 \
+    int bxr_instance_weights_bwd_##SUF(const T* logits, const T* grad_spatial_w, const T* grad_level_w,             \
+                                       long long rows, int L, int K, T* grad_logits, bxr_stream_t stream) {         \
+        g_launches = 0;                                                                                              \
+        g_detail[0] = 0;                                                                                             \
+        if (rows < 0 || L < 0 || K < 0 || L > BXR_MAX_LEVELS || (K & 1)) return fail(BXR_ERR_BAD_DIM, "rows, L >= 0, L <= 32, K even"); \
+        if (rows == 0 || L == 0) return BXR_OK;                                                                      \
+        if (!logits || !grad_logits || (K > 0 && (!grad_spatial_w || !grad_level_w)))                                \
+            return fail(BXR_ERR_NULL_POINTER, "pointer is NULL");                                                    \
+        long long blocks = (rows + 7) / 8;                                                                           \
+        if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();                                                  \
+        inst_weights_bwd_kernel<T><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(                      \
+            logits, grad_spatial_w, grad_level_w, grad_logits, rows, L, K);                                          \
+        BXR_CUDA(cudaGetLastError());                                                                                \
+        ++g_launches;                                                                                                \
+        return BXR_OK;                                                                                               \
+    }
+
 #define BXR_DEFINE_SMAX_FWD(SUF, TVABI, TV, TW)                                                                      \
     int bxr_box_grid_softmax_attn_fwd_##SUF(const TVABI* value, const int64_t* shapes, const int64_t* level_start,   \
                                             const TW* boxes, const TW* angles, const TW* valid_ratios,               \
@@ -895,10 +930,22 @@ size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, i
 #if BXR_TU_DTYPES & 1
 BXR_FWD(f32, float, float, float)
 BXR_BWD(f32, float, float, float)
+#if BXR_TU_DIRS & 1
+BXR_DEFINE_INSTW_FWD(f32, float)
+#endif
+#if BXR_TU_DIRS & 2
+BXR_DEFINE_INSTW_BWD(f32, float)
+#endif
 #endif
 #if BXR_TU_DTYPES & 2
 BXR_FWD(f64, double, double, double)
 BXR_BWD(f64, double, double, double)
+#if BXR_TU_DIRS & 1
+BXR_DEFINE_INSTW_FWD(f64, double)
+#endif
+#if BXR_TU_DIRS & 2
+BXR_DEFINE_INSTW_BWD(f64, double)
+#endif
 #endif
 #if BXR_TU_DTYPES & 4
 BXR_FWD(bf16, bxr_bf16, __nv_bfloat16, float)

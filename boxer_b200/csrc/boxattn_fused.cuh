@@ -119,4 +119,94 @@ __global__ void softmax_bwd_rows_kernel(const TW* __restrict__ w, TW* __restrict
     }
 }
 
+// ---- InstanceAttention's weights from its 2 x 2 logit map per (head, level) (SURVEY.md 8 row f2;
+// e2edet/module/box_attention.py:93-110): the map is nearest-upsampled to K x K (repeat_interleave), then
+//   spatial_w = softmax over all (L, K, K) entries,    level_w = softmax over L at every (i, j).
+// With r = (K/2)^2 copies of each logit:  spatial_w = exp(z - m) / (r * sum_{l,q} exp(z - m)),
+// level_w = exp(z - m_q) / sum_l exp(z_lq - m_q)  per quadrant q.  One warp per (b, query, head) row.
+constexpr int kInstWMaxLogits = 4 * kMaxLevels;
+
+template <typename T>
+__device__ __forceinline__ void inst_row_weights(const T* __restrict__ z, int L, int K, int lane, T* s_sw, T* s_lw) {
+    // every lane derives the (tiny) statistics itself; lanes share the per-(l, q) results through shared memory
+    const int n = 4 * L;
+    T m = -INFINITY, mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int t = 0; t < n; ++t) {
+        const T v = z[t];
+        m = v > m ? v : m;
+        mq[t & 3] = v > mq[t & 3] ? v : mq[t & 3];
+    }
+    T sum = 0, sq[4] = {0, 0, 0, 0};
+    for (int t = 0; t < n; ++t) {
+        sum += exp(z[t] - m);
+        sq[t & 3] += exp(z[t] - mq[t & 3]);
+    }
+    const T r = (T)((K / 2) * (K / 2));
+    for (int t = lane; t < n; t += 32) {
+        s_sw[t] = exp(z[t] - m) / (r * sum);
+        s_lw[t] = exp(z[t] - mq[t & 3]) / sq[t & 3];
+    }
+    __syncwarp();
+}
+
+template <typename T>
+__global__ void inst_weights_fwd_kernel(const T* __restrict__ logits, T* __restrict__ spatial_w, T* __restrict__ level_w,
+                                        long long rows, int L, int K) {
+    __shared__ T s_sw[8][kInstWMaxLogits], s_lw[8][kInstWMaxLogits];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int KK = K * K, half = K / 2, n_out = L * KK;
+    for (long long row = warp; row < rows; row += nwarps) {
+        inst_row_weights<T>(logits + row * 4 * L, L, K, lane, s_sw[wid], s_lw[wid]);
+        for (int idx = lane; idx < n_out; idx += 32) {
+            const int l = idx / KK, rem = idx - l * KK, i = rem / K, j = rem - i * K;
+            const int t = l * 4 + (i >= half ? 2 : 0) + (j >= half ? 1 : 0);
+            spatial_w[row * n_out + idx] = s_sw[wid][t];
+            level_w[row * n_out + idx] = s_lw[wid][t];
+        }
+        __syncwarp();
+    }
+}
+
+// grad_logits[l, q] = s_lq (Gs_lq - r * sum_{l',q'} s_l'q' Gs_l'q') + w_lq (Gl_lq - sum_l' w_l'q Gl_l'q)
+// with Gs / Gl the gradients of spatial_w / level_w summed over the quadrant's (K/2)^2 entries.
+template <typename T>
+__global__ void inst_weights_bwd_kernel(const T* __restrict__ logits, const T* __restrict__ grad_sw, const T* __restrict__ grad_lw,
+                                        T* __restrict__ grad_logits, long long rows, int L, int K) {
+    __shared__ T s_sw[8][kInstWMaxLogits], s_lw[8][kInstWMaxLogits], s_gs[8][kInstWMaxLogits], s_gl[8][kInstWMaxLogits];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int KK = K * K, half = K / 2, n_out = L * KK, r = half * half, n = 4 * L;
+    for (long long row = warp; row < rows; row += nwarps) {
+        inst_row_weights<T>(logits + row * n, L, K, lane, s_sw[wid], s_lw[wid]);
+        for (int t = 0; t < n; ++t) {
+            const int l = t >> 2, a = (t >> 1) & 1, b = t & 1;
+            T ps = 0, pl = 0;
+            for (int e = lane; e < r; e += 32) {
+                const int i = a * half + e / half, j = b * half + e % half;
+                const long long idx = row * n_out + l * KK + i * K + j;
+                ps += grad_sw[idx];
+                pl += grad_lw[idx];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ps += __shfl_xor_sync(0xffffffffu, ps, o);
+                pl += __shfl_xor_sync(0xffffffffu, pl, o);
+            }
+            if (lane == 0) { s_gs[wid][t] = ps; s_gl[wid][t] = pl; }
+        }
+        __syncwarp();
+        T ds = 0;
+        for (int t = 0; t < n; ++t) ds += s_sw[wid][t] * s_gs[wid][t];
+        for (int t = lane; t < n; t += 32) {
+            T dl = 0;
+            for (int l2 = 0; l2 < L; ++l2) dl += s_lw[wid][l2 * 4 + (t & 3)] * s_gl[wid][l2 * 4 + (t & 3)];
+            grad_logits[row * n + t] = s_sw[wid][t] * (s_gs[wid][t] - (T)r * ds) + s_lw[wid][t] * (s_gl[wid][t] - dl);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace bxr

@@ -360,3 +360,48 @@ def box_grid_attn_backward(value, spatial_shapes, level_start_index, boxes, angl
             grad_attn.data_ptr(), ws.data_ptr() if ws is not None else None, n, flags, _stream(value.device))
     _native.check(st, "box_grid_attn_backward")
     return [grad_value, grad_boxes, grad_angles, grad_attn]
+
+
+# ============================================================== InstanceAttention weights from the 2x2 logit maps
+def _instw_geometry(logits, K):
+    _check_input(logits, "logits")
+    if logits.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f"instance weights support float32 and float64 logits, got {logits.dtype}")
+    if logits.dim() != 6 or logits.shape[-1] != 2 or logits.shape[-2] != 2:
+        raise RuntimeError(f"logits must be (B, Nq, heads, L, 2, 2), got {tuple(logits.shape)}")
+    K = int(K)
+    if K < 0 or K % 2:
+        raise RuntimeError(f"kernel size must be even (the 2x2 map is upsampled by K/2), got {K}")
+    B, Nq, H, L = logits.shape[:4]
+    if L > 32:
+        raise RuntimeError("at most 32 levels are supported")
+    return B * Nq * H, L, K, "f32" if logits.dtype == torch.float32 else "f64"
+
+
+def instance_weights_forward(logits, K):
+    """(spatial_w, level_w), each (B,Nq,H,L,K,K), from InstanceAttention's (B,Nq,H,L,2,2) logit maps:
+    nearest-upsample to K x K, softmax over (L,K,K) / over L (box_attention.py:93-110) -- one kernel."""
+    rows, L, K, suf = _instw_geometry(logits, K)
+    shape = tuple(logits.shape[:4]) + (K, K)
+    sw = torch.empty(shape, dtype=logits.dtype, device=logits.device)
+    lw = torch.empty_like(sw)
+    with _on_device(logits.device):
+        st = _fn(f"bxr_instance_weights_fwd_{suf}")(logits.data_ptr(), rows, L, K, sw.data_ptr(), lw.data_ptr(),
+                                                    _stream(logits.device))
+    _native.check(st, "instance_weights_forward")
+    return sw, lw
+
+
+def instance_weights_backward(logits, grad_spatial_w, grad_level_w, K):
+    """gradient of the logits given the gradients of both weight tensors -- one kernel."""
+    rows, L, K, suf = _instw_geometry(logits, K)
+    for g, n in ((grad_spatial_w, "grad_spatial_w"), (grad_level_w, "grad_level_w")):
+        _check_input(g, n)
+        if g.dtype != logits.dtype or g.numel() != rows * L * K * K or g.device != logits.device:
+            raise RuntimeError(f"{n} must match the weights' dtype, size and device")
+    grad = torch.empty_like(logits)
+    with _on_device(logits.device):
+        st = _fn(f"bxr_instance_weights_bwd_{suf}")(logits.data_ptr(), grad_spatial_w.data_ptr(), grad_level_w.data_ptr(),
+                                                    rows, L, K, grad.data_ptr(), _stream(logits.device))
+    _native.check(st, "instance_weights_backward")
+    return grad

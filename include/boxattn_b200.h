@@ -180,6 +180,23 @@ BXR_DECLARE_SMAX(f32, float, float)
 BXR_DECLARE_SMAX(f64, double, double)
 BXR_DECLARE_SMAX(bf16, bxr_bf16, float)
 
+/*
+ * InstanceAttention's two weight tensors from its 2 x 2 logit map per (head, level).
+ * Replaces, in one launch each way, the chain in e2edet/module/box_attention.py:93-110:
+ *   view(B,Nq,H,L,2,2) -> repeat_interleave(K/2) x2 -> softmax over (L,K,K) = spatial_w; softmax over L = level_w
+ * and its autograd backward.
+ *   logits (rows, L, 2, 2), rows = B*Nq*H;  spatial_w / level_w (rows, L, K, K);  K even.  fp32 / fp64 only
+ *   (the weights are fp32 in every mode of the ops above).
+ */
+#define BXR_DECLARE_INSTW(SUF, T)                                                                                  \
+    int bxr_instance_weights_fwd_##SUF(const T* logits, long long rows, int L, int K, T* spatial_w, T* level_w,   \
+                                       bxr_stream_t stream);                                                       \
+    int bxr_instance_weights_bwd_##SUF(const T* logits, const T* grad_spatial_w, const T* grad_level_w,           \
+                                       long long rows, int L, int K, T* grad_logits, bxr_stream_t stream);
+
+BXR_DECLARE_INSTW(f32, float)
+BXR_DECLARE_INSTW(f64, double)
+
 #ifdef __cplusplus
 }
 #endif

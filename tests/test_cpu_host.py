@@ -20,7 +20,8 @@ def _header_symbols():
     names -= {n for n in names if n.endswith("_")}           # macro stems: bxr_box_attn_fwd_##SUF
     for macro, ops in (("BXR_DECLARE_OPS", ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd")),
                        ("BXR_DECLARE_FUSED", ("box_grid_attn_fwd", "box_grid_attn_bwd")),
-                       ("BXR_DECLARE_SMAX", ("box_grid_softmax_attn_fwd", "box_grid_softmax_attn_bwd"))):
+                       ("BXR_DECLARE_SMAX", ("box_grid_softmax_attn_fwd", "box_grid_softmax_attn_bwd")),
+                       ("BXR_DECLARE_INSTW", ("instance_weights_fwd", "instance_weights_bwd"))):
         for op in ops:
             for suf in re.findall(macro + r"\((\w+),", text):
                 if suf != "SUF":

@@ -275,3 +275,81 @@ def test_modules_with_fused_softmax_match_reference_modules(case):
     assert helpers.rel_err(out_f, out_d) <= 2e-5
     for n in g_d:
         assert helpers.rel_err(g_f[n], g_d[n]) <= 2e-4, n
+
+
+# ================================================================== InstanceAttention weights (row f2, second half)
+def _torch_instance_weights(z, K):
+    """the reference's chain, box_attention.py:93-110"""
+    b, nq, h, L = z.shape[:4]
+    a = z.repeat_interleave(K // 2, dim=-1).repeat_interleave(K // 2, dim=-2)
+    sw = torch.softmax(a.reshape(b, nq, h, -1), -1).view(b, nq, h, L, K, K)
+    lw = torch.softmax(a.view(b, nq, h, L, K, K), dim=3)
+    return sw, lw
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-6)], ids=["f64", "f32"])
+@pytest.mark.parametrize("L,K", [(4, 14), (1, 2), (3, 4), (4, 28), (9, 6)])
+def test_instance_weights_match_reference_chain(L, K, dtype, tol):
+    import boxer_b200
+    g = torch.Generator().manual_seed(100 * L + K)
+    z64 = 3.0 * torch.randn(2, 7, 3, L, 2, 2, generator=g, dtype=torch.float64)
+    gs = torch.randn(2, 7, 3, L, K, K, generator=g, dtype=torch.float64)
+    gl = torch.randn(2, 7, 3, L, K, K, generator=g, dtype=torch.float64)
+    zr = z64.clone().requires_grad_(True)
+    sw_r, lw_r = _torch_instance_weights(zr, K)
+    (sw_r * gs).sum().add((lw_r * gl).sum()).backward()
+
+    z = z64.to(DEV, dtype).requires_grad_(True)
+    sw, lw = boxer_b200.InstanceWeightsFunction.apply(z, K)
+    assert sw.shape == sw_r.shape and lw.shape == lw_r.shape
+    ((sw * gs.to(DEV, dtype)).sum() + (lw * gl.to(DEV, dtype)).sum()).backward()
+    assert helpers.rel_err(sw, sw_r.detach()) <= tol
+    assert helpers.rel_err(lw, lw_r.detach()) <= tol
+    assert helpers.rel_err(z.grad, zr.grad) <= max(tol, 1e-12) * 10
+
+
+def test_instance_weights_reject_odd_kernel_and_empty_is_fine():
+    import boxer_b200
+    with pytest.raises(RuntimeError, match="even"):
+        boxer_b200.ops.instance_weights_forward(torch.zeros(1, 1, 1, 1, 2, 2, device=DEV), 3)
+    sw, lw = boxer_b200.ops.instance_weights_forward(torch.zeros(1, 0, 2, 3, 2, 2, device=DEV), 4)
+    assert sw.shape == (1, 0, 2, 3, 4, 4) and lw.numel() == 0
+
+
+@pytest.mark.parametrize("case", ["inst_train", "inst_infer"])
+def test_instance_module_with_fused_weights_matches_reference_module(case):
+    import boxer_b200
+    spec = refinputs.module_cases()[case]
+    gold = helpers.golden("modules_golden")[case]
+    mod = getattr(boxer_b200, spec["cls"])(**spec["ctor"]).double()
+    state = {k[len("param_"):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("param_")}
+    mod.load_state_dict(state, strict=True)
+    mod = mod.to(DEV, torch.float32)
+    mod.inferencing = spec["inferencing"]
+    args = [a.to(DEV, torch.float32) if (torch.is_tensor(a) and a.is_floating_point()) else (a.to(DEV) if torch.is_tensor(a) else a)
+            for a in refinputs.module_inputs(spec)]
+
+    def run(fused):
+        mod.zero_grad()
+        boxer_b200.set_fused_softmax(fused)
+        try:
+            outs = mod(*args)
+            loss = outs[0].square().sum()
+            if outs[1] is not None:
+                loss = loss + outs[1].square().sum()
+            loss.backward()
+        finally:
+            boxer_b200.set_fused_softmax(False)
+        flat = []
+        for o in outs:
+            if o is not None:
+                flat.extend(o if isinstance(o, tuple) else [o])
+        return [f.detach() for f in flat], {n: p.grad.clone() for n, p in mod.named_parameters()}
+
+    flat_f, g_f = run(True)
+    flat_d, g_d = run(False)
+    assert len(flat_f) == int(gold["n_out"])
+    for i, o in enumerate(flat_f):
+        assert helpers.rel_err(o, gold[f"out{i}"]) <= 1e-4, (case, i)
+    for n in g_d:
+        assert helpers.rel_err(g_f[n], g_d[n]) <= 2e-4, n
