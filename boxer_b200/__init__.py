@@ -15,13 +15,14 @@ from .box_attention import (Box3dAttention, BoxAttention, InstanceAttention, set
                             set_fused_softmax)
 from .box_attention_func import (BoxAttnBf16Function, BoxAttnFunction, BoxGridAttnBf16Function, BoxGridAttnFunction,
                                  BoxGridSoftmaxAttnBf16Function, BoxGridSoftmaxAttnFunction,
-                                 InstanceAttnBf16Function, InstanceAttnFunction, InstanceWeightsFunction)
+                                 InstanceAttnBf16Function, InstanceAttnFunction, InstanceWeightsFunction,
+                                 ValueEpilogueFunction)
 from .ops import set_deterministic
 
 __all__ = [
     "BoxAttnFunction", "InstanceAttnFunction", "BoxAttnBf16Function", "InstanceAttnBf16Function",
     "BoxAttention", "InstanceAttention", "Box3dAttention",
-    "BoxGridAttnFunction", "BoxGridAttnBf16Function", "BoxGridSoftmaxAttnFunction", "BoxGridSoftmaxAttnBf16Function", "InstanceWeightsFunction",
+    "BoxGridAttnFunction", "BoxGridAttnBf16Function", "BoxGridSoftmaxAttnFunction", "BoxGridSoftmaxAttnBf16Function", "InstanceWeightsFunction", "ValueEpilogueFunction",
     "ops", "compat", "set_deterministic", "set_amp_native", "set_fused_grid", "set_fused_softmax",
 ]
 __version__ = "0.1.0"

@@ -39,7 +39,7 @@ OPS = ("box_attn_fwd", "box_attn_bwd", "instance_attn_fwd", "instance_attn_bwd")
 FUSED_OPS = ("box_grid_attn_fwd", "box_grid_attn_bwd", "box_grid_softmax_attn_fwd", "box_grid_softmax_attn_bwd")
 EXPORTS = (
     ["bxr_abi_version", "bxr_status_string", "bxr_last_error_detail", "bxr_last_launch_count",
-     "bxr_attn_bwd_workspace_bytes", "bxr_box_grid_attn_workspace_bytes"]
+     "bxr_attn_bwd_workspace_bytes", "bxr_box_grid_attn_workspace_bytes", "bxr_value_epilogue"]
     + [f"bxr_{op}_{dt}" for op in OPS + FUSED_OPS for dt in DTYPES]
     + [f"bxr_instance_weights_{d}_{dt}" for d in ("fwd", "bwd") for dt in ("f32", "f64")]
 )
@@ -130,6 +130,8 @@ def _declare(lib):
         f.restype, f.argtypes = i, [vp, c.c_longlong, i, i, vp, vp, vp]
         f = getattr(lib, f"bxr_instance_weights_bwd_{dt}")
         f.restype, f.argtypes = i, [vp, vp, vp, c.c_longlong, i, i, vp, vp]
+    lib.bxr_value_epilogue.restype = i
+    lib.bxr_value_epilogue.argtypes = [vp, i, vp, vp, i, c.c_longlong, i, vp]
     lib.bxr_box_grid_attn_workspace_bytes.restype = c.c_size_t
     lib.bxr_box_grid_attn_workspace_bytes.argtypes = [c.c_int] * 9 + [c.c_uint]
     return lib

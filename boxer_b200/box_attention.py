@@ -30,7 +30,8 @@ import torch.nn.functional as F
 
 from .box_attention_func import (BoxAttnBf16Function, BoxAttnFunction, BoxGridAttnBf16Function, BoxGridAttnFunction,
                                  BoxGridSoftmaxAttnBf16Function, BoxGridSoftmaxAttnFunction,
-                                 InstanceAttnBf16Function, InstanceAttnFunction, InstanceWeightsFunction)
+                                 InstanceAttnBf16Function, InstanceAttnFunction, InstanceWeightsFunction,
+                                 ValueEpilogueFunction)
 
 _AMP_NATIVE = False
 _FUSED_GRID = False
@@ -193,7 +194,10 @@ class _BoxAttentionBase(nn.Module):
     def _project_value(self, value, v_mask):
         b, l2 = value.shape[:2]
         value = self.value_proj(value)
-        if v_mask is not None:
+        if _use_bf16(value) and value.dtype in (torch.float32, torch.bfloat16):
+            # bf16-native ops: mask fill + cast to the gather's storage type in one pass
+            value = ValueEpilogueFunction.apply(value, v_mask, torch.bfloat16)
+        elif v_mask is not None:
             value = value.masked_fill(v_mask[..., None], float(0))
         return value.view(b, l2, self.num_head, self.head_dim)
 

@@ -150,6 +150,23 @@ class BoxGridSoftmaxAttnFunction(Function):
         return gv, None, None, gb, ga, None, None, gz, None
 
 
+class ValueEpilogueFunction(Function):
+    """``apply(projected_value (B,S,C), v_mask (B,S) bool | None, out_dtype)``: padding-mask fill + storage cast in one
+    pass (box_attention.py:222-225); the gradient is masked and cast back the same way."""
+
+    @staticmethod
+    def forward(ctx, value, mask, out_dtype):
+        ctx.in_dtype = value.dtype
+        ctx.mask = mask
+        return ops.value_epilogue(value.contiguous(), mask.contiguous() if mask is not None else None, out_dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        mask = ctx.mask
+        return ops.value_epilogue(grad.contiguous(), mask.contiguous() if mask is not None else None, ctx.in_dtype), None, None
+
+
 class InstanceWeightsFunction(Function):
     """``apply(logits (B,Nq,H,L,2,2), kernel_size) -> (spatial_w, level_w)``, each (B,Nq,H,L,K,K): InstanceAttention's
     ``repeat_interleave`` x2 + softmax over (L,K,K) + softmax over L (box_attention.py:93-110) and their backward as

@@ -764,6 +764,25 @@ int fused_backward(const TV* value, const int64_t* shapes, const int64_t* level_
     return BXR_OK;
 }
 
+// value_proj epilogue: mask fill + storage cast in one pass (boxattn_fused.cuh)
+template <typename TI, typename TO>
+int value_epilogue(const void* in, const unsigned char* mask, void* out, long long rows, int C, bxr_stream_t stream) {
+    g_launches = 0;
+    g_detail[0] = 0;
+    if (rows < 0 || C < 0) return fail(BXR_ERR_BAD_DIM, "negative dimension");
+    if (rows == 0 || C == 0) return BXR_OK;
+    if (!in || !out) return fail(BXR_ERR_NULL_POINTER, "pointer is NULL");
+    const int vec = (C % 8 == 0 && aligned16(in) && aligned16(out)) ? 1 : 0;
+    const long long n = vec ? rows * (C / 8) : rows * C;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    value_epilogue_kernel<TI, TO><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const TI*>(in), mask, static_cast<TO*>(out), rows, C, vec);
+    BXR_CUDA(cudaGetLastError());
+    ++g_launches;
+    return BXR_OK;
+}
+
 }  // namespace BXR_SLICE_NS
 
 using namespace BXR_SLICE_NS;
@@ -796,6 +815,14 @@ size_t bxr_attn_bwd_workspace_bytes(int dtype_bytes, int B, int S, int H, int D,
 size_t bxr_box_grid_attn_workspace_bytes(int dtype_bytes, int backward, int B, int S, int H, int D, int L, int Nq, int P,
                                          unsigned flags) {
     return fused_workspace_bytes(dtype_bytes, backward, B, S, H, D, L, Nq, P, flags);
+}
+int bxr_value_epilogue(const void* in, int in_bytes, const unsigned char* mask, void* out, int out_bytes, long long rows,
+                       int C, bxr_stream_t stream) {
+    if (in_bytes == 4 && out_bytes == 4) return value_epilogue<float, float>(in, mask, out, rows, C, stream);
+    if (in_bytes == 4 && out_bytes == 2) return value_epilogue<float, __nv_bfloat16>(in, mask, out, rows, C, stream);
+    if (in_bytes == 2 && out_bytes == 4) return value_epilogue<__nv_bfloat16, float>(in, mask, out, rows, C, stream);
+    if (in_bytes == 2 && out_bytes == 2) return value_epilogue<__nv_bfloat16, __nv_bfloat16>(in, mask, out, rows, C, stream);
+    return fail(BXR_ERR_UNSUPPORTED, "value epilogue: element sizes must be 4 (float) or 2 (bfloat16)");
 }
 #endif  // BXR_TU_COMMON
 

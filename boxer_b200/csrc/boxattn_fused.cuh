@@ -209,4 +209,48 @@ __global__ void inst_weights_bwd_kernel(const T* __restrict__ logits, const T* _
     }
 }
 
+// ---- value_proj epilogue (e2edet/module/box_attention.py:222-225): padding-mask fill and the
+// cast to the storage type the gather wants, in one pass over the projected value:
+//   out[r, :] = mask[r] ? 0 : (TO) in[r, :]          r = (b, s) pixel, C = heads * head_dim channels
+// (the (B,S,C) -> (B,S,H,D) "head-major" step is a view).  The backward is the same kernel with the types swapped.
+template <typename T> struct Chan8;
+template <> struct Chan8<float> {
+    __device__ static void load(const float* p, float (&v)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    __device__ static void store(float* p, const float (&v)[8]) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct Chan8<__nv_bfloat16> {
+    __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) { Vec16<__nv_bfloat16>::load(p, v); }
+    __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) { Vec16<__nv_bfloat16>::store(p, v); }
+};
+
+template <typename TI, typename TO>
+__global__ void value_epilogue_kernel(const TI* __restrict__ in, const unsigned char* __restrict__ mask, TO* __restrict__ out,
+                                      long long rows, int C, int vec) {
+    if (vec) {       // C % 8 == 0 and 16-byte aligned rows: 8 channels per thread
+        const int per_row = C / 8;
+        const long long n = rows * per_row;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+            const long long r = t / per_row;
+            float v[8];
+            if (mask && mask[r]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            } else {
+                Chan8<TI>::load(in + t * 8, v);
+            }
+            Chan8<TO>::store(out + t * 8, v);
+        }
+    } else {
+        const long long n = rows * C;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+            out[t] = (mask && mask[t / C]) ? from_f<TO, float>(0.f) : from_f<TO, float>(to_f(in[t]));
+    }
+}
+
 }  // namespace bxr

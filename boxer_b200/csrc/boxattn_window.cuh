@@ -161,7 +161,7 @@ __device__ __forceinline__ RowSoftmax row_softmax(const float* __restrict__ logi
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gm, mx, o));
     float sum = 0.f;
-    for (int i = lane; i < LP; i += G) sum += expf(__ldg(logits + i) - mx);
+    for (int i = lane; i < LP; i += G) sum += __expf(__ldg(logits + i) - mx);     // ex2.approx: 2 ulp, inside the 1e-4 bar
     sum = gsum<G>(sum, gm);
     RowSoftmax r;
     r.mx = mx;
@@ -179,7 +179,7 @@ __device__ __forceinline__ LanePoint lane_point_box(const LevelBox& q, const flo
     float x, y;
     box_point(q, k.x, k.y, x, y);
     float aw = __ldg(w_l + pc);
-    if (SMAX) aw = expf(aw - sm.mx) * sm.inv;
+    if (SMAX) aw = __expf(aw - sm.mx) * sm.inv;
     return lane_point_xy(x, y, aw, act, h, w);
 }
 

@@ -405,3 +405,24 @@ def instance_weights_backward(logits, grad_spatial_w, grad_level_w, K):
                                                     rows, L, K, grad.data_ptr(), _stream(logits.device))
     _native.check(st, "instance_weights_backward")
     return grad
+
+
+# ============================================================== value_proj epilogue: mask fill + storage cast
+def value_epilogue(value, mask, out_dtype):
+    """``value.masked_fill(mask[..., None], 0).to(out_dtype)`` in one pass (box_attention.py:222-225 + the cast the
+    bf16 ops want).  value (..., C) float32 / bfloat16; mask (...) bool or None."""
+    _check_input(value, "value")
+    if value.dtype not in (torch.float32, torch.bfloat16) or out_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("value epilogue supports float32 and bfloat16")
+    C = value.shape[-1] if value.dim() else 1
+    rows = value.numel() // C if C else 0
+    if mask is not None:
+        _check_input(mask, "mask")
+        if mask.dtype != torch.bool or mask.numel() != rows or mask.device != value.device:
+            raise RuntimeError("mask must be a bool tensor with one entry per pixel, on value's device")
+    out = torch.empty(value.shape, dtype=out_dtype, device=value.device)
+    with _on_device(value.device):
+        st = _fn("bxr_value_epilogue")(value.data_ptr(), value.element_size(), mask.data_ptr() if mask is not None else None,
+                                       out.data_ptr(), out.element_size(), rows, C, _stream(value.device))
+    _native.check(st, "value_epilogue")
+    return out

@@ -188,6 +188,15 @@ BXR_DECLARE_SMAX(bf16, bxr_bf16, float)
  *   logits (rows, L, 2, 2), rows = B*Nq*H;  spatial_w / level_w (rows, L, K, K);  K even.  fp32 / fp64 only
  *   (the weights are fp32 in every mode of the ops above).
  */
+/*
+ * value_proj epilogue (e2edet/module/box_attention.py:222-225): padding-mask fill + cast to the
+ * storage type of the gather in one pass:  out[r, :] = mask[r] ? 0 : cast(in[r, :]),  r over rows = B*S pixels.
+ *   in / out: float (element bytes 4) or bfloat16 (2), C channels per pixel;  mask: rows bytes (bool), or NULL.
+ * Its backward is the same call with grad_out as `in` and the input's type as the output type.
+ */
+int bxr_value_epilogue(const void* in, int in_bytes, const unsigned char* mask, void* out, int out_bytes, long long rows,
+                       int C, bxr_stream_t stream);
+
 #define BXR_DECLARE_INSTW(SUF, T)                                                                                  \
     int bxr_instance_weights_fwd_##SUF(const T* logits, long long rows, int L, int K, T* spatial_w, T* level_w,   \
                                        bxr_stream_t stream);                                                       \

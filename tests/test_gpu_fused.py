@@ -353,3 +353,47 @@ def test_instance_module_with_fused_weights_matches_reference_module(case):
         assert helpers.rel_err(o, gold[f"out{i}"]) <= 1e-4, (case, i)
     for n in g_d:
         assert helpers.rel_err(g_f[n], g_d[n]) <= 2e-4, n
+
+
+# ================================================================== value_proj epilogue (row f3)
+@pytest.mark.parametrize("C", [256, 30])
+@pytest.mark.parametrize("din,dout", [(torch.float32, torch.bfloat16), (torch.float32, torch.float32),
+                                      (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("masked", [True, False])
+def test_value_epilogue_is_masked_fill_plus_cast(C, din, dout, masked):
+    """bit-exact vs ``value.masked_fill(mask[..., None], 0).to(dtype)`` (box_attention.py:222-225), forward and backward."""
+    import boxer_b200
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(2, 301, C, generator=g).to(DEV, din).requires_grad_(True)
+    mask = (torch.rand(2, 301, generator=g) < 0.3).to(DEV) if masked else None
+    out = boxer_b200.ValueEpilogueFunction.apply(x, mask, dout)
+    ref_in = x.detach().clone().requires_grad_(True)
+    ref = (ref_in.masked_fill(mask[..., None], 0.0) if masked else ref_in).to(dout)
+    assert out.dtype == dout and torch.equal(out, ref)
+    go = torch.randn(2, 301, C, generator=g).to(DEV, dout)
+    out.backward(go)
+    ref.backward(go)
+    assert x.grad.dtype == din and torch.equal(x.grad, ref_in.grad)
+
+
+def test_bf16_native_module_uses_the_value_epilogue_and_matches_fp32():
+    """BoxAttention under set_amp_native(True) + autocast (value masked and cast by the epilogue kernel) vs the
+    default fp32 path: bf16 tolerance on the output, same masked pixels."""
+    import boxer_b200
+    spec = refinputs.module_cases()["box_3d_refs_masked"]
+    gold = helpers.golden("modules_golden")["box_3d_refs_masked"]
+    mod = boxer_b200.BoxAttention(**spec["ctor"]).double()
+    mod.load_state_dict({k[len("param_"):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("param_")}, strict=True)
+    mod = mod.to(DEV, torch.float32)
+    args = [a.to(DEV, torch.float32) if (torch.is_tensor(a) and a.is_floating_point()) else (a.to(DEV) if torch.is_tensor(a) else a)
+            for a in refinputs.module_inputs(spec)]
+    ref = mod(*args)[0]
+    boxer_b200.set_amp_native(True)
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = mod(*args)[0]
+            out.float().sum().backward()
+    finally:
+        boxer_b200.set_amp_native(False)
+    assert helpers.rel_err(out.float(), ref) <= 2e-2
+    assert mod.value_proj.weight.grad is not None and bool(torch.isfinite(mod.value_proj.weight.grad).all())
