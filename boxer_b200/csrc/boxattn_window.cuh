@@ -214,6 +214,22 @@ __device__ __forceinline__ float ssum(float v, unsigned m) {
     return v;
 }
 
+// All groups of a warp walk the level loop together (rows past the end are carried along as inactive), so the
+// reductions and barriers that sit outside mode-dependent branches use the full warp mask: a partial-mask
+// shuffle / __syncwarp compiles to a MATCH.ANY + REDUX + VOTE + BRA.DIV convergence check in front of it.
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// zero the first n4 (multiple of 4) words of a CAP-word window: SUB lanes, 16-byte stores, no loop
+template <int SUB, int CAP, typename T>
+__device__ __forceinline__ void zero_window(T* win, int n4, int slane) {
+    static_assert(sizeof(T) == 4, "window slots are 32-bit");
+#pragma unroll
+    for (int j = 0; j < (CAP + SUB * 4 - 1) / (SUB * 4); ++j) {
+        const int s = (j * SUB + slane) * 4;
+        if (s < n4) *reinterpret_cast<uint4*>(win + s) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // what every lane of the group needs to know about one level of the current pass
 struct SubWin {
     int X0, Y0, nx, ny;   // touched pixel range (clamped to the level); nx <= 0: nothing inside
@@ -250,8 +266,9 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
     // units are dealt round-robin: rows of the coarse levels (wide windows -> per-point fallback) cost
     // several times more than level-0 rows, and a contiguous split leaves the CTAs that own them as a tail
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const long long row = (long long)u * GROUPS + gid;
-        if (row >= p.rows) continue;            // whole group leaves; everything below is group-scoped
+        const long long row_raw = (long long)u * GROUPS + gid;
+        const bool ract = row_raw < p.rows;     // groups past the last row stay with their warp, doing nothing
+        const long long row = ract ? row_raw : 0;
         const int head = (int)(row % p.H);
         const long long b = row / ((long long)p.H * p.Nq);
         // value addressing in 16-byte units (one lane chunk) as 32-bit indices off the tensor base
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
         const float* w_row = w0 + row * p.LP;
         RowSoftmax rsm;
         rsm.mx = 0.f; rsm.inv = 1.f;
-        if constexpr (SMAX) rsm = row_softmax<G>(w_row, p.LP, lane, gm);
+        if constexpr (SMAX) rsm = row_softmax<G>(w_row, p.LP, lane, kFullMask);
 
         float acc[VEC];
 #pragma unroll
@@ -269,8 +286,8 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
         for (int l0 = 0; l0 < p.L; l0 += LPP) {
             // ---- A: own points of my level, touched pixel range (reductions stay inside the SUB lanes)
             const int lm = l0 + sub;
-            const bool lact = lm < p.L;
-            const int lmc = lact ? lm : 0;
+            const bool lact = ract && lm < p.L;
+            const int lmc = lm < p.L ? lm : 0;
             const int mh = lv.h[lmc], mw = lv.w[lmc];
             LanePoint pt[PPL];
             int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
@@ -292,38 +309,39 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
                 }
             }
             SubWin me;
-            me.X0 = max(smin<SUB>(bx0, gm), 0); me.Y0 = max(smin<SUB>(by0, gm), 0);
-            me.nx = min(smax<SUB>(bx1, gm), mw - 1) - me.X0 + 1;
-            me.ny = min(smax<SUB>(by1, gm), mh - 1) - me.Y0 + 1;
-            S = ssum<SUB>(S, gm);
+            me.X0 = max(smin<SUB>(bx0, kFullMask), 0); me.Y0 = max(smin<SUB>(by0, kFullMask), 0);
+            me.nx = min(smax<SUB>(bx1, kFullMask), mw - 1) - me.X0 + 1;
+            me.ny = min(smax<SUB>(by1, kFullMask), mh - 1) - me.Y0 + 1;
+            S = ssum<SUB>(S, kFullMask);
             const int nq = me.nx * me.ny;
             // non-finite weights (S is NaN/inf) take the float path so that they propagate
             me.mode = (me.nx <= 0 || me.ny <= 0 || S == 0.f) ? 0 : ((nq <= CAP && S <= 3.0e38f) ? 1 : 2);
             me.ke = fixed_scale_exp(S);
 
             // ---- B: scatter pixel weights into my level's dense nx x ny window (32-bit fixed point)
+            if (me.mode == 1) zero_window<SUB, CAP>(win, (nq + 3) & ~3, slane);
+            __syncwarp();
             if (me.mode == 1) {
                 const float scale = pow2f(me.ke);
-                for (int s = slane; s < ((nq + 3) & ~3); s += SUB) win[s] = 0;
-                __syncwarp(gm);                  // (masked __syncwarp tolerates the divergence between sub-groups)
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     if (pt[k].inside) {
                         const int sx = pt[k].x0 - me.X0, sy = pt[k].y0 - me.Y0;   // -1 .. n-1
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
-                        const float a = pt[k].aw * scale;
+                        const float ax = pt[k].aw * scale * hx, bx = pt[k].aw * scale * pt[k].lx;
+                        // the four corner weights first, so that each guarded body is a single predicated atomic
+                        const int w00 = __float2int_rn(hy * ax), w01 = __float2int_rn(hy * bx);
+                        const int w10 = __float2int_rn(pt[k].ly * ax), w11 = __float2int_rn(pt[k].ly * bx);
                         const bool vx0 = sx >= 0, vx1 = sx + 1 < me.nx, vy0 = sy >= 0, vy1 = sy + 1 < me.ny;
                         int* wp = win + sy * me.nx + sx;
-                        if (vy0 && vx0) atomicAdd(wp, __float2int_rn(hy * hx * a));
-                        if (vy0 && vx1) atomicAdd(wp + 1, __float2int_rn(hy * pt[k].lx * a));
-                        if (vy1 && vx0) atomicAdd(wp + me.nx, __float2int_rn(pt[k].ly * hx * a));
-                        if (vy1 && vx1) atomicAdd(wp + me.nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a));
+                        if (vy0 && vx0) atomicAdd(wp, w00);
+                        if (vy0 && vx1) atomicAdd(wp + 1, w01);
+                        if (vy1 && vx0) atomicAdd(wp + me.nx, w10);
+                        if (vy1 && vx1) atomicAdd(wp + me.nx + 1, w11);
                     }
                 }
-            } else {
-                __syncwarp(gm);
             }
-            __syncwarp(gm);
+            __syncwarp();
 
             // ---- C: all G lanes walk the window(s) of this pass
 #pragma unroll
@@ -333,9 +351,9 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
                     w = me;
                 } else {
                     const int src = sl * SUB;
-                    w.X0 = __shfl_sync(gm, me.X0, src, G); w.Y0 = __shfl_sync(gm, me.Y0, src, G);
-                    w.nx = __shfl_sync(gm, me.nx, src, G); w.ny = __shfl_sync(gm, me.ny, src, G);
-                    w.ke = __shfl_sync(gm, me.ke, src, G); w.mode = __shfl_sync(gm, me.mode, src, G);
+                    w.X0 = __shfl_sync(kFullMask, me.X0, src, G); w.Y0 = __shfl_sync(kFullMask, me.Y0, src, G);
+                    w.nx = __shfl_sync(kFullMask, me.nx, src, G); w.ny = __shfl_sync(kFullMask, me.ny, src, G);
+                    w.ke = __shfl_sync(kFullMask, me.ke, src, G); w.mode = __shfl_sync(kFullMask, me.mode, src, G);
                 }
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
@@ -406,9 +424,9 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
                     }
                 }
             }
-            __syncwarp(gm);   // the windows are re-zeroed by the next pass
+            __syncwarp();   // the windows are re-zeroed by the next pass
         }
-        V::store(static_cast<TV*>(p.out) + (row * p.D + lane * VEC), acc);
+        if (ract) V::store(static_cast<TV*>(p.out) + (row * p.D + lane * VEC), acc);
     }
 }
 
@@ -487,8 +505,9 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
     if constexpr (DET) dscale = *p.det_scale;
 
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const long long row = (long long)u * GROUPS + gid;
-        if (row >= p.rows) continue;
+        const long long row_raw = (long long)u * GROUPS + gid;
+        const bool ract = row_raw < p.rows;     // groups past the last row stay with their warp, doing nothing
+        const long long row = ract ? row_raw : 0;
         const int head = (int)(row % p.H);
         const long long b = row / ((long long)p.H * p.Nq);
         const unsigned vbase = (unsigned)(b * p.S * HDV + head * G + lane);
@@ -499,8 +518,8 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
 
         for (int l0 = 0; l0 < p.L; l0 += LPP) {
             const int lm = l0 + sub;
-            const bool lact = lm < p.L;
-            const int lmc = lact ? lm : 0;
+            const bool lact = ract && lm < p.L;
+            const int lmc = lm < p.L ? lm : 0;
             const int mh = lv.h[lmc], mw = lv.w[lmc];
             LanePoint pt[PPL];
             float g_a[PPL], g_x[PPL], g_y[PPL];     // this lane's results for its own points
@@ -521,10 +540,10 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
                 }
             }
             SubWin me;
-            me.X0 = max(smin<SUB>(bx0, gm), 0); me.Y0 = max(smin<SUB>(by0, gm), 0);
-            me.nx = min(smax<SUB>(bx1, gm), mw - 1) - me.X0 + 1;
-            me.ny = min(smax<SUB>(by1, gm), mh - 1) - me.Y0 + 1;
-            S = ssum<SUB>(S, gm);
+            me.X0 = max(smin<SUB>(bx0, kFullMask), 0); me.Y0 = max(smin<SUB>(by0, kFullMask), 0);
+            me.nx = min(smax<SUB>(bx1, kFullMask), mw - 1) - me.X0 + 1;
+            me.ny = min(smax<SUB>(by1, kFullMask), mh - 1) - me.Y0 + 1;
+            S = ssum<SUB>(S, kFullMask);
             const int nq = me.nx * me.ny;
             me.mode = (me.nx <= 0 || me.ny <= 0) ? 0 : ((nq <= CAP && S <= 3.0e38f) ? 1 : 2);
             me.ke = fixed_scale_exp(fmaxf(S, 1e-30f));
@@ -533,27 +552,30 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
             //    "touched" flag (1.0) until C overwrites it with the dot products: a pixel touched with zero
             //    total weight still needs its d.
             if (me.mode == 1) {
+                zero_window<SUB, CAP>(win, (nq + 3) & ~3, slane);
+                zero_window<SUB, CAP>(dot, (nq + 3) & ~3, slane);
+            }
+            __syncwarp();
+            if (me.mode == 1) {
                 const float scale = pow2f(me.ke);
-                for (int s = slane; s < ((nq + 3) & ~3); s += SUB) { win[s] = 0; dot[s] = 0.f; }
-                __syncwarp(gm);
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     if (pt[k].inside) {
                         const int sx = pt[k].x0 - me.X0, sy = pt[k].y0 - me.Y0;
                         const float hx = 1.f - pt[k].lx, hy = 1.f - pt[k].ly;
-                        const float a = pt[k].aw * scale;
+                        const float ax = pt[k].aw * scale * hx, bx = pt[k].aw * scale * pt[k].lx;
+                        const int w00 = __float2int_rn(hy * ax), w01 = __float2int_rn(hy * bx);
+                        const int w10 = __float2int_rn(pt[k].ly * ax), w11 = __float2int_rn(pt[k].ly * bx);
                         const bool vx0 = sx >= 0, vx1 = sx + 1 < me.nx, vy0 = sy >= 0, vy1 = sy + 1 < me.ny;
                         const int s00 = sy * me.nx + sx;
-                        if (vy0 && vx0) { atomicAdd(win + s00, __float2int_rn(hy * hx * a)); dot[s00] = 1.f; }
-                        if (vy0 && vx1) { atomicAdd(win + s00 + 1, __float2int_rn(hy * pt[k].lx * a)); dot[s00 + 1] = 1.f; }
-                        if (vy1 && vx0) { atomicAdd(win + s00 + me.nx, __float2int_rn(pt[k].ly * hx * a)); dot[s00 + me.nx] = 1.f; }
-                        if (vy1 && vx1) { atomicAdd(win + s00 + me.nx + 1, __float2int_rn(pt[k].ly * pt[k].lx * a)); dot[s00 + me.nx + 1] = 1.f; }
+                        if (vy0 && vx0) { atomicAdd(win + s00, w00); dot[s00] = 1.f; }
+                        if (vy0 && vx1) { atomicAdd(win + s00 + 1, w01); dot[s00 + 1] = 1.f; }
+                        if (vy1 && vx0) { atomicAdd(win + s00 + me.nx, w10); dot[s00 + me.nx] = 1.f; }
+                        if (vy1 && vx1) { atomicAdd(win + s00 + me.nx + 1, w11); dot[s00 + me.nx + 1] = 1.f; }
                     }
                 }
-            } else {
-                __syncwarp(gm);
             }
-            __syncwarp(gm);
+            __syncwarp();
 
             // C: all G lanes walk the window(s) of this pass
 #pragma unroll
@@ -563,9 +585,9 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
                     w = me;
                 } else {
                     const int src = sl * SUB;
-                    w.X0 = __shfl_sync(gm, me.X0, src, G); w.Y0 = __shfl_sync(gm, me.Y0, src, G);
-                    w.nx = __shfl_sync(gm, me.nx, src, G); w.ny = __shfl_sync(gm, me.ny, src, G);
-                    w.ke = __shfl_sync(gm, me.ke, src, G); w.mode = __shfl_sync(gm, me.mode, src, G);
+                    w.X0 = __shfl_sync(kFullMask, me.X0, src, G); w.Y0 = __shfl_sync(kFullMask, me.Y0, src, G);
+                    w.nx = __shfl_sync(kFullMask, me.nx, src, G); w.ny = __shfl_sync(kFullMask, me.ny, src, G);
+                    w.ke = __shfl_sync(kFullMask, me.ke, src, G); w.mode = __shfl_sync(kFullMask, me.mode, src, G);
                 }
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
@@ -660,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
                     }
                 }
             }
-            __syncwarp(gm);
+            __syncwarp();
             // D: finish own points from the d window of my level
             if (me.mode == 1) {
 #pragma unroll
@@ -680,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
                     }
                 }
             }
-            __syncwarp(gm);
+            __syncwarp();
             // coalesced stores of this pass's gradients (zeros for points outside the window test)
             if (lact) {
 #pragma unroll
@@ -711,9 +733,9 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
                         ba += gx * (-ux * lbx.sn - uy * lbx.cs) + gy * (ux * lbx.cs - uy * lbx.sn);
                     }
                 }
-                bcx = ssum<SUB>(bcx, gm); bcy = ssum<SUB>(bcy, gm);
-                bw = ssum<SUB>(bw, gm); bh = ssum<SUB>(bh, gm);
-                if (p.grad_angles) ba = ssum<SUB>(ba, gm);
+                bcx = ssum<SUB>(bcx, kFullMask); bcy = ssum<SUB>(bcy, kFullMask);
+                bw = ssum<SUB>(bw, kFullMask); bh = ssum<SUB>(bh, kFullMask);
+                if (p.grad_angles) ba = ssum<SUB>(ba, kFullMask);
                 if (lact && slane == 0) {
                     const long long rl = row * p.L + lm;
                     reinterpret_cast<float4*>(p.grad_boxes)[rl] =
@@ -725,12 +747,14 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
         if constexpr (SMAX) {
             // the row's weight gradients were written by the lanes of this group: read them back (L2) after a
             // group barrier and chain them through the softmax, in place
-            __syncwarp(gm);
+            __syncwarp();
             float* gw = grad_w0 + row * p.LP;
             float dotp = 0.f;
-            for (int i = lane; i < p.LP; i += G) dotp += __ldg(w_row + i) * __ldcg(gw + i);
-            dotp = gsum<G>(dotp, gm);
-            for (int i = lane; i < p.LP; i += G) gw[i] = __ldg(w_row + i) * (__ldcg(gw + i) - dotp);
+            if (ract)
+                for (int i = lane; i < p.LP; i += G) dotp += __ldg(w_row + i) * __ldcg(gw + i);
+            dotp = gsum<G>(dotp, kFullMask);
+            if (ract)
+                for (int i = lane; i < p.LP; i += G) gw[i] = __ldg(w_row + i) * (__ldcg(gw + i) - dotp);
         }
     }
 }

@@ -77,11 +77,18 @@ def _check_input(t, name):
         raise RuntimeError(f"{name} must be contiguous")
 
 
+_GEOMETRY_NAMES = ("value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight[0]", "attn_weight[1]")
+
+
 def _geometry(value, shapes, lsi, loc, weights):
-    for t, n in ((value, "value"), (shapes, "spatial_shapes"), (lsi, "level_start_index"), (loc, "sampling_loc")):
-        _check_input(t, n)
-    for i, w in enumerate(weights):
-        _check_input(w, f"attn_weight[{i}]")
+    tensors = (value, shapes, lsi, loc, *weights)
+    try:        # one pass on the hot path; the per-tensor diagnosis only when something is off
+        ok = all(t.is_cuda and t.is_contiguous() for t in tensors)
+    except AttributeError:
+        ok = False
+    if not ok:
+        for t, n in zip(tensors, _GEOMETRY_NAMES):
+            _check_input(t, n)
     if value.dim() != 4:
         raise RuntimeError(f"value must be (B, S, heads, head_dim), got {tuple(value.shape)}")
     if shapes.dtype != torch.int64 or lsi.dtype != torch.int64:
@@ -102,9 +109,10 @@ def _geometry(value, shapes, lsi, loc, weights):
                 f"attention weights must hold B*Nq*heads*L*P = {B * Nq * H * L * P} elements, got {tuple(w.shape)}")
     if L > 32:
         raise RuntimeError("at most 32 levels are supported")
-    devs = {t.device for t in (value, shapes, lsi, loc, *weights)}
-    if len(devs) != 1:
-        raise RuntimeError(f"all tensors must be on the same device, got {sorted(map(str, devs))}")
+    dev = value.device
+    for t in tensors:
+        if t.device != dev:
+            raise RuntimeError(f"all tensors must be on the same device, got {sorted({str(x.device) for x in tensors})}")
     return B, S, H, D, L, Nq, P
 
 
@@ -126,7 +134,13 @@ def _step_check(B, im2col_step):
         raise RuntimeError(f"batch({B}) must divide im2col_step({step})")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(dev):
+    # decoder-sized calls are launch-latency bound: the raw-handle query is ~20x cheaper than building a Stream object
+    if _raw_stream is not None:
+        return _raw_stream(dev.index if dev.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(dev).cuda_stream
 
 
