@@ -68,13 +68,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and not is_stale():
             return LIB_PATH
         os.makedirs(LIB_DIR, exist_ok=True)
-        objdir = os.path.join(os.environ.get("TMPDIR", "/tmp"), "boxattn_b200_build")   # objects stay out of the tree
+        objdir = os.path.join(os.environ.get("TMPDIR", "/tmp"), "boxattn_b200_build" + ("_alt" if os.environ.get("BOXER_B200_LIB") else ""))   # objects stay out of the tree
         os.makedirs(objdir, exist_ok=True)
         nvcc = _nvcc()
+        extra = os.environ.get("BOXER_B200_NVCC_EXTRA", "").split()      # experiment hook: -D tuning macros for A/B builds
         procs = []
         for name, dtypes, dirs, common in SLICES:
             obj = os.path.join(objdir, name + ".o")
-            cmd = [nvcc, *NVCC_FLAGS, f"-DBXR_TU_DTYPES={dtypes}", f"-DBXR_TU_DIRS={dirs}", f"-DBXR_TU_COMMON={common}", f"-DBXR_TU_NAME={name}",
+            cmd = [nvcc, *NVCC_FLAGS, *extra, f"-DBXR_TU_DTYPES={dtypes}", f"-DBXR_TU_DIRS={dirs}", f"-DBXR_TU_COMMON={common}", f"-DBXR_TU_NAME={name}",
                    "-c", "-o", obj, *SOURCES]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")

@@ -313,6 +313,10 @@ bool fused_applies(int dtype_bytes, int B, int S, int H, int D, int L, int P, un
     return true;
 }
 
+#ifndef BXR_INST_BWD_BF16X4
+#define BXR_INST_BWD_BF16X4 1
+#endif
+
 // ---- owner-tap instance kernels (boxattn_instance.cuh)
 constexpr int kInstLevels = 4;
 bool use_inst_own(const AttnParams& p, int g, unsigned flags) {
@@ -550,6 +554,17 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
             }
         } else if (own) {
             if constexpr (INSTANCE) {
+#if BXR_INST_BWD_BF16X4
+                // bf16, head_dim 32: 8-byte lanes (G = 8, 4 channels per lane) halve the per-lane register load of the
+                // 16-byte-lane kernel, which spills at 128 registers
+                if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
+                    if (bf16_lane8_group(D) == 8 && use_inst_own(p, 8, flags))
+                        return (status = det ? bwd_inst_own<bf16x4_t, 8, long long>(p, st) : bwd_inst_own<bf16x4_t, 8, float>(p, st))
+                                   ? status
+                                   : (det ? finalize<TV, long long>(static_cast<const long long*>(acc), grad_value, n_value, scale, st)
+                                          : finalize<TV, float>(static_cast<const float*>(acc), grad_value, n_value, nullptr, st));
+                }
+#endif
                 if (g == 8) status = det ? bwd_inst_own<TV, 8, long long>(p, st) : bwd_inst_own<TV, 8, float>(p, st);
                 else status = det ? bwd_inst_own<TV, 4, long long>(p, st) : bwd_inst_own<TV, 4, float>(p, st);
             }

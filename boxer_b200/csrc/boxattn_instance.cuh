@@ -39,11 +39,17 @@ __device__ __forceinline__ BTap bcast_tap(const LanePoint& t, float lw, int src,
     return b;
 }
 
-// LB: levels held in registers per lane (L <= LB)
+#ifndef BXR_INST_LG
+#define BXR_INST_LG 2
+#endif
+
+// LB: levels held in registers per lane (L <= LB); LG: levels whose corner rows are in flight together
 template <typename TV, int G, int LB>
 __global__ void __launch_bounds__(kThreads, 2) inst_fwd_own_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
+    constexpr int LG = BXR_INST_LG;
+    static_assert(LB % LG == 0, "level batches must tile LB");
     constexpr int GROUPS = kThreads / G;
     __shared__ LevelTable lv;
     __shared__ float s_red[kThreads * VEC];
@@ -104,32 +110,42 @@ __global__ void __launch_bounds__(kThreads, 2) inst_fwd_own_kernel(const AttnPar
                     float macc[VEC];
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) macc[i] = 0.f;
+                    // levels in batches of LG: all 4*LG corner rows are requested (in storage form) before the
+                    // first is used -- the walk is a chain of dependent gathers, memory-level parallelism is what
+                    // it runs on (one level at a time left the kernel 5x above its issue bound)
 #pragma unroll
-                    for (int l = 0; l < LB; ++l) {
-                        if (l >= p.L) break;
-                        const BTap t = bcast_tap<G>(tp[l], lwv[l], o, gm);
-                        if (!t.inside) continue;
-                        const int lh = lv.h[l], lw = lv.w[l];
-                        const float hx = 1.f - t.lx, hy = 1.f - t.ly;
-                        const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= lw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
-                        const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
-                        const float cw[4] = {hy * hx, hy * t.lx, t.ly * hx, t.ly * t.lx};
-                        const unsigned c00 = vrow + ((unsigned)lv.start[l] + (unsigned)(t.y0 * lw + t.x0)) * HDV;
-                        float v[4][VEC];
+                    for (int l0 = 0; l0 < LB; l0 += LG) {
+                        if (l0 >= p.L) break;
+                        typename V::Raw raw[LG][4];
+                        float cw[LG][4], wsp[LG], wlv[LG];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (ok[k]) {
-                                V::load16(value16, c00 + ((k & 1) ? HDV : 0u) + ((k & 2) ? (unsigned)lw * HDV : 0u), v[k]);
-                            } else {
+                        for (int j = 0; j < LG; ++j) {
+                            const int l = l0 + j;
+                            const BTap t = bcast_tap<G>(tp[l], lwv[l], o, gm);      // (levels >= L carry inside = false)
+                            const int lh = lv.h[l < p.L ? l : 0], lw = lv.w[l < p.L ? l : 0];
+                            const float hx = 1.f - t.lx, hy = 1.f - t.ly;
+                            const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= lw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
+                            const bool ok[4] = {t.inside && vy0 && vx0, t.inside && vy0 && vx1, t.inside && vy1 && vx0, t.inside && vy1 && vx1};
+                            cw[j][0] = hy * hx; cw[j][1] = hy * t.lx; cw[j][2] = t.ly * hx; cw[j][3] = t.ly * t.lx;
+                            wsp[j] = t.sw; wlv[j] = t.lw;
+                            const unsigned c00 = vrow + ((unsigned)lv.start[l < p.L ? l : 0] + (unsigned)(t.y0 * lw + t.x0)) * HDV;
 #pragma unroll
-                                for (int i = 0; i < VEC; ++i) v[k][i] = 0.f;
+                            for (int k = 0; k < 4; ++k) {
+                                raw[j][k] = V::zero_raw();
+                                if (ok[k]) raw[j][k] = V::load_raw(value16, c00 + ((k & 1) ? HDV : 0u) + ((k & 2) ? (unsigned)lw * HDV : 0u));
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) {
-                            const float val = cw[0] * v[0][i] + cw[1] * v[1][i] + cw[2] * v[2][i] + cw[3] * v[3][i];
-                            acc[i] += val * t.sw;       // instance_attn_kernel.cuh:354
-                            macc[i] += val * t.lw;      // :355
+                        for (int j = 0; j < LG; ++j) {
+                            float v[4][VEC];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) V::unpack_raw(raw[j][k], v[k]);
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) {
+                                const float val = cw[j][0] * v[0][i] + cw[j][1] * v[1][i] + cw[j][2] * v[2][i] + cw[j][3] * v[3][i];
+                                acc[i] += val * wsp[j];       // instance_attn_kernel.cuh:354
+                                macc[i] += val * wlv[j];      // :355
+                            }
                         }
                     }
                     V::store(mrow + (long long)(p0 + o) * HD, macc);
@@ -155,10 +171,16 @@ __global__ void __launch_bounds__(kThreads, 2) inst_fwd_own_kernel(const AttnPar
     }
 }
 
+#ifndef BXR_INST_BWD_LG
+#define BXR_INST_BWD_LG 2
+#endif
+
 template <typename TV, int G, int LB, typename ACC>
 __global__ void __launch_bounds__(kThreads, 2) inst_bwd_own_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
+    constexpr int LG = (VEC > 4) ? 1 : BXR_INST_BWD_LG;     // 8 channels per lane: no registers left for a second level (A/B, r01q)
+    static_assert(LB % LG == 0, "level batches must tile LB");
     constexpr int GROUPS = kThreads / G;
     constexpr bool DET = sizeof(ACC) == 8;
     __shared__ LevelTable lv;
@@ -221,48 +243,66 @@ __global__ void __launch_bounds__(kThreads, 2) inst_bwd_own_kernel(const AttnPar
             for (int o = 0; o < n_here; ++o) {
                 float gmv[VEC];
                 V::load(gmrow + (long long)(p0 + o) * HD, gmv);
+                // levels in batches of LG: the corner rows of the whole batch are requested before the first is used
 #pragma unroll
-                for (int l = 0; l < LB; ++l) {
-                    if (l >= p.L) break;
-                    const BTap t = bcast_tap<G>(tp[l], lwv[l], o, gm);
-                    if (!t.inside) continue;
-                    const int lh = lv.h[l], lw = lv.w[l];
-                    const float hx = 1.f - t.lx, hy = 1.f - t.ly;
-                    const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= lw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
-                    const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
-                    const float cw[4] = {hy * hx, hy * t.lx, t.ly * hx, t.ly * t.lx};
-                    const unsigned c00 = vrow + ((unsigned)lv.start[l] + (unsigned)(t.y0 * lw + t.x0)) * HDV;
-                    float tg[VEC];
+                for (int l0 = 0; l0 < LB; l0 += LG) {
+                    if (l0 >= p.L) break;
+                    typename V::Raw raw[LG][4];
+                    unsigned offs[LG];
+                    BTap tb[LG];
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) tg[i] = go[i] * t.sw + gmv[i] * t.lw;    // instance_attn_kernel.cuh:139
-                    float v[4][VEC];
+                    for (int j = 0; j < LG; ++j) {
+                        const int l = l0 + j;
+                        tb[j] = bcast_tap<G>(tp[l], lwv[l], o, gm);             // (levels >= L carry inside = false)
+                        const BTap& t = tb[j];
+                        const int lc = l < p.L ? l : 0;
+                        const int lh = lv.h[lc], lw = lv.w[lc];
+                        const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= lw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
+                        const bool ok[4] = {t.inside && vy0 && vx0, t.inside && vy0 && vx1, t.inside && vy1 && vx0, t.inside && vy1 && vx1};
+                        offs[j] = vrow + ((unsigned)lv.start[lc] + (unsigned)(t.y0 * lw + t.x0)) * HDV;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned off = c00 + ((k & 1) ? HDV : 0u) + ((k & 2) ? (unsigned)lw * HDV : 0u);
-                        if (ok[k]) {
-                            V::load16(value16, off, v[k]);
-                            scatter_row<ACC, VEC>(gacc + (size_t)off * VEC, tg, cw[k], dscale);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) v[k][i] = 0.f;
+                        for (int k = 0; k < 4; ++k) {
+                            raw[j][k] = V::zero_raw();
+                            if (ok[k]) raw[j][k] = V::load_raw(value16, offs[j] + ((k & 1) ? HDV : 0u) + ((k & 2) ? (unsigned)lw * HDV : 0u));
                         }
                     }
-                    float d[4] = {0.f, 0.f, 0.f, 0.f};    // d spatial_w, d level_w, d x, d y (partials over my channels)
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float val = cw[0] * v[0][i] + cw[1] * v[1][i] + cw[2] * v[2][i] + cw[3] * v[3][i];
-                        d[0] += go[i] * val;                                                  // :183
-                        d[1] += gmv[i] * val;                                                 // :184
-                        d[2] += (hy * (v[1][i] - v[0][i]) + t.ly * (v[3][i] - v[2][i])) * tg[i];
-                        d[3] += (hx * (v[2][i] - v[0][i]) + t.lx * (v[3][i] - v[1][i])) * tg[i];
-                    }
+                    for (int j = 0; j < LG; ++j) {
+                        const int l = l0 + j;
+                        const BTap& t = tb[j];
+                        if (!t.inside) continue;                                  // uniform in the group
+                        const int lh = lv.h[l], lw = lv.w[l];
+                        const float hx = 1.f - t.lx, hy = 1.f - t.ly;
+                        const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= lw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
+                        const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
+                        const float cw[4] = {hy * hx, hy * t.lx, t.ly * hx, t.ly * t.lx};
+                        float tg[VEC];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) d[k] = gsum<G>(d[k], gm);
-                    if (lane == o) {
-                        r_s[l] = d[0];
-                        r_l[l] = d[1];
-                        r_x[l] = (float)lw * d[2];
-                        r_y[l] = (float)lh * d[3];
+                        for (int i = 0; i < VEC; ++i) tg[i] = go[i] * t.sw + gmv[i] * t.lw;    // instance_attn_kernel.cuh:139
+                        float v[4][VEC];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            V::unpack_raw(raw[j][k], v[k]);
+                            const unsigned off = offs[j] + ((k & 1) ? HDV : 0u) + ((k & 2) ? (unsigned)lw * HDV : 0u);
+                            if (ok[k]) scatter_row<ACC, VEC>(gacc + (size_t)off * VEC, tg, cw[k], dscale);
+                        }
+                        float d[4] = {0.f, 0.f, 0.f, 0.f};    // d spatial_w, d level_w, d x, d y (partials over my channels)
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            const float val = cw[0] * v[0][i] + cw[1] * v[1][i] + cw[2] * v[2][i] + cw[3] * v[3][i];
+                            d[0] += go[i] * val;                                                  // :183
+                            d[1] += gmv[i] * val;                                                 // :184
+                            d[2] += (hy * (v[1][i] - v[0][i]) + t.ly * (v[3][i] - v[2][i])) * tg[i];
+                            d[3] += (hx * (v[2][i] - v[0][i]) + t.lx * (v[3][i] - v[1][i])) * tg[i];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) d[k] = gsum<G>(d[k], gm);
+                        if (lane == o) {
+                            r_s[l] = d[0];
+                            r_l[l] = d[1];
+                            r_x[l] = (float)lw * d[2];
+                            r_y[l] = (float)lh * d[3];
+                        }
                     }
                 }
             }

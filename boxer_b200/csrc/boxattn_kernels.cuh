@@ -97,6 +97,13 @@ template <> struct Vec16<float> {
         const uint4 t = __ldg(static_cast<const uint4*>(base) + idx);
         v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
     }
+    // the same load kept in its storage form, so that many can be in flight before the first is unpacked
+    using Raw = uint4;
+    __device__ __forceinline__ static Raw zero_raw() { return make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ static Raw load_raw(const void* base, unsigned idx) { return __ldg(static_cast<const uint4*>(base) + idx); }
+    __device__ __forceinline__ static void unpack_raw(const Raw& t, float (&v)[4]) {
+        v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+    }
 };
 template <> struct Vec16<__nv_bfloat16> {
     static constexpr int VEC = 8;
@@ -111,6 +118,17 @@ template <> struct Vec16<__nv_bfloat16> {
     }
     __device__ __forceinline__ static void load16(const void* base, unsigned idx, float (&v)[8]) {
         const uint4 t = __ldg(static_cast<const uint4*>(base) + idx);
+        const unsigned u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(u[i] << 16);
+            v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+        }
+    }
+    using Raw = uint4;
+    __device__ __forceinline__ static Raw zero_raw() { return make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ static Raw load_raw(const void* base, unsigned idx) { return __ldg(static_cast<const uint4*>(base) + idx); }
+    __device__ __forceinline__ static void unpack_raw(const Raw& t, float (&v)[8]) {
         const unsigned u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -144,6 +162,10 @@ template <> struct Vec16<bf16x4_t> {
     __device__ __forceinline__ static void load16(const void* base, unsigned idx, float (&v)[4]) {   // idx in 8-byte units
         unpack(__ldg(static_cast<const uint2*>(base) + idx), v);
     }
+    using Raw = uint2;
+    __device__ __forceinline__ static Raw zero_raw() { return make_uint2(0u, 0u); }
+    __device__ __forceinline__ static Raw load_raw(const void* base, unsigned idx) { return __ldg(static_cast<const uint2*>(base) + idx); }
+    __device__ __forceinline__ static void unpack_raw(const Raw& t, float (&v)[4]) { unpack(t, v); }
     __device__ __forceinline__ static void store(bf16x4_t* p, const float (&v)[4]) {
         const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
         *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
