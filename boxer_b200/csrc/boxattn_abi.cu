@@ -80,20 +80,20 @@ int sm_count() {
     return cache[dev];
 }
 
-template <void (*K)(const AttnParams)>
+template <void (*K)(const AttnParams), int THREADS = kThreads>
 int ctas_per_sm() {
     static int occ = 0;   // immutable once set; a benign race only recomputes the same number
     if (occ == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, kThreads, 0) != cudaSuccess || n <= 0) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, THREADS, 0) != cudaSuccess || n <= 0) n = 1;
         occ = n;
     }
     return occ;
 }
 
-template <void (*K)(const AttnParams)>
+template <void (*K)(const AttnParams), int THREADS = kThreads>
 int launch(const AttnParams& p, int grid, cudaStream_t st, const char* name) {
-    K<<<grid, kThreads, 0, st>>>(p);
+    K<<<grid, THREADS, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, name);
     ++g_launches;
@@ -138,12 +138,12 @@ void choose_split(AttnParams& p, int G, int lim, int min_chunk) {
     p.units = (int)((p.rows + rows_per_unit - 1) / rows_per_unit);
 }
 
-template <void (*K)(const AttnParams)>
+template <void (*K)(const AttnParams), int THREADS = kThreads>
 int launch_units(const AttnParams& p, cudaStream_t st, const char* name) {
-    int grid = sm_count() * ctas_per_sm<K>();
+    int grid = sm_count() * ctas_per_sm<K, THREADS>();
     if (grid > p.units) grid = p.units;
     if (grid < 1) grid = 1;
-    return launch<K>(p, grid, st, name);
+    return launch<K, THREADS>(p, grid, st, name);
 }
 
 template <void (*K)(const AttnParams)>
@@ -212,13 +212,13 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
 
 template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX>
 int fwd_win(AttnParams& p, cudaStream_t st) {
-    p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED, SMAX>>(p, st, "box_fwd_win_kernel");
+    p.units = (int)((p.rows + kWinThreads / G - 1) / (kWinThreads / G));
+    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED, SMAX>, kWinThreads>(p, st, "box_fwd_win_kernel");
 }
 template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX>
 int bwd_win(AttnParams& p, cudaStream_t st) {
-    p.units = (int)((p.rows + kThreads / G - 1) / (kThreads / G));
-    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED, SMAX>>(p, st, "box_bwd_win_kernel");
+    p.units = (int)((p.rows + kWinThreads / G - 1) / (kWinThreads / G));
+    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED, SMAX>, kWinThreads>(p, st, "box_bwd_win_kernel");
 }
 
 // (G, SUB, PPL): SUB lanes share a level's points, PPL points per lane; P <= SUB * PPL.

@@ -42,10 +42,15 @@ __device__ __forceinline__ BTap bcast_tap(const LanePoint& t, float lw, int src,
 #ifndef BXR_INST_LG
 #define BXR_INST_LG 2
 #endif
+// resident CTAs per SM (A/B r01q): the fp32 forward gains 8-11 % from a third CTA (85 registers), the bf16
+// forward (8 channels per lane) and both backwards lose to the spills
+#ifndef BXR_INST_FWD_MINB_F32
+#define BXR_INST_FWD_MINB_F32 3
+#endif
 
 // LB: levels held in registers per lane (L <= LB); LG: levels whose corner rows are in flight together
 template <typename TV, int G, int LB>
-__global__ void __launch_bounds__(kThreads, 2) inst_fwd_own_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_INST_FWD_MINB_F32) inst_fwd_own_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
     constexpr int LG = BXR_INST_LG;

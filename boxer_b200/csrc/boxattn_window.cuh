@@ -40,6 +40,20 @@ namespace bxr {
 #define BXR_FB_UNROLL 1   // unroll factor of the per-point fallback loop
 #endif
 
+// CTA size of the window kernels: a work unit is one CTA's worth of rows, and with ~12 units per CTA the last
+// unit's quantum is the tail of the launch -- smaller CTAs, smaller quantum (A/B: profiles/README.md)
+#ifndef BXR_WIN_THREADS
+#define BXR_WIN_THREADS 256
+#endif
+constexpr int kWinThreads = BXR_WIN_THREADS;
+constexpr int kWinCtaScale = kThreads / kWinThreads;      // resident-CTA targets below are stated for 256 threads
+
+// Work units are dealt round-robin from the LAST one down: in BoxeR's encoder the trailing queries belong to the
+// coarse levels, whose rows cost several times more (wide footprints -> per-point walk); starting with them leaves
+// the cheap units for the tail of the launch (A/B r01q: forward 0.1875 -> 0.1844 ms; harmless for other inputs).
+#ifndef BXR_UNIT_REVERSE
+#define BXR_UNIT_REVERSE 1
+#endif
 constexpr int kFbUnroll = BXR_FB_UNROLL;
 constexpr int kWinSide = 8;
 constexpr int kWinSlots = kWinSide * kWinSide;
@@ -241,12 +255,12 @@ struct SubWin {
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
 // SMAX (with FUSED): `w0` holds logits; the softmax over the row's L*P points is taken here and written to attn_out.
 template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX = false>
-__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_MINB) box_fwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_MINB) * kWinCtaScale) box_fwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax prologue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
-    constexpr int GROUPS = kThreads / G;
+    constexpr int GROUPS = kWinThreads / G;
     constexpr int LPP = GEO::LPP, CAP = GEO::CAP;
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];
@@ -265,7 +279,11 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_M
 
     // units are dealt round-robin: rows of the coarse levels (wide windows -> per-point fallback) cost
     // several times more than level-0 rows, and a contiguous split leaves the CTAs that own them as a tail
+#if BXR_UNIT_REVERSE
+    for (int u = p.units - 1 - (int)blockIdx.x; u >= 0; u -= gridDim.x) {
+#else
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+#endif
         const long long row_raw = (long long)u * GROUPS + gid;
         const bool ract = row_raw < p.rows;     // groups past the last row stay with their warp, doing nothing
         const long long row = ract ? row_raw : 0;
@@ -473,12 +491,12 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
 // SMAX (with FUSED): `w0` holds the softmax weights the forward wrote; the weight gradients are chained through
 // the softmax before they leave the kernel:  grad_logit = w * (grad_w - sum_row(w * grad_w)).
 template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX = false>
-__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_MINB) box_bwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_MINB) * kWinCtaScale) box_bwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax epilogue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
-    constexpr int GROUPS = kThreads / G;
+    constexpr int GROUPS = kWinThreads / G;
     constexpr int LPP = GEO::LPP, CAP = GEO::CAP;
     constexpr bool DET = sizeof(ACC) == 8;
     __shared__ LevelTable lv;
@@ -504,7 +522,11 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_M
     float dscale = 1.f;
     if constexpr (DET) dscale = *p.det_scale;
 
+#if BXR_UNIT_REVERSE
+    for (int u = p.units - 1 - (int)blockIdx.x; u >= 0; u -= gridDim.x) {
+#else
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+#endif
         const long long row_raw = (long long)u * GROUPS + gid;
         const bool ract = row_raw < p.rows;     // groups past the last row stay with their warp, doing nothing
         const long long row = ract ? row_raw : 0;
