@@ -316,6 +316,9 @@ bool fused_applies(int dtype_bytes, int B, int S, int H, int D, int L, int P, un
 #ifndef BXR_INST_BWD_BF16X4
 #define BXR_INST_BWD_BF16X4 1
 #endif
+#ifndef BXR_INST_FWD_BF16X4
+#define BXR_INST_FWD_BF16X4 0
+#endif
 
 // ---- owner-tap instance kernels (boxattn_instance.cuh)
 constexpr int kInstLevels = 4;
@@ -399,6 +402,11 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
                 if (use_window(p, g, flags))
                     return use_staged(p, g, 0, 1, flags) ? dispatch_fwd_stg<TV, 0>(g, p, st) : dispatch_fwd_win<TV>(g, p, st);
             } else {
+#if BXR_INST_FWD_BF16X4
+                if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
+                    if (bf16_lane8_group(D) == 8 && use_inst_own(p, 8, flags)) return fwd_inst_own<bf16x4_t, 8>(p, st);
+                }
+#endif
                 if (use_inst_own(p, g, flags)) return g == 8 ? fwd_inst_own<TV, 8>(p, st) : fwd_inst_own<TV, 4>(p, st);
             }
             return dispatch_fwd_vec<TV, INSTANCE>(g, p, st);

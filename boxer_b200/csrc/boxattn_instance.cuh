@@ -244,10 +244,15 @@ __global__ void __launch_bounds__(kThreads, 2) inst_bwd_own_kernel(const AttnPar
                 }
             }
             const int n_here = min(G, p.P - p0);
+            // grad_mask is a DRAM stream read once: the next point's row is requested while this point is worked on
+            const typename V::Raw* gmraw = reinterpret_cast<const typename V::Raw*>(gmrow);
+            const long long gm_pitch = HD / VEC;
+            typename V::Raw gm_next = __ldg(gmraw + (long long)p0 * gm_pitch);
 #pragma unroll 1
             for (int o = 0; o < n_here; ++o) {
                 float gmv[VEC];
-                V::load(gmrow + (long long)(p0 + o) * HD, gmv);
+                V::unpack_raw(gm_next, gmv);
+                if (o + 1 < n_here) gm_next = __ldg(gmraw + (long long)(p0 + o + 1) * gm_pitch);
                 // levels in batches of LG: the corner rows of the whole batch are requested before the first is used
 #pragma unroll
                 for (int l0 = 0; l0 < LB; l0 += LG) {
