@@ -17,17 +17,17 @@ timeout 300 python scripts/compare_reference_cuda.py $OUT/vs_reference_cuda.json
 if [ "$MODE" != "quick" ]; then
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:attn_|box_|absmax|finalize|det_scale" -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source off -k "regex:attn_fwd_vec|box_fwd_win" -s 2 -c 1 -f -o $OUT/fwd_enc_K4 \
+timeout 400 ncu --set full --clock-control none --import-source on -k "regex:attn_fwd_vec|box_fwd_win" -s 2 -c 1 -f -o $OUT/fwd_enc_K4 \
     python scripts/prof_driver.py --workload enc --K 4 > $OUT/ncu_fwd.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source off -k "regex:attn_bwd_vec|box_bwd_win" -s 2 -c 1 -f -o $OUT/bwd_enc_K4 \
+timeout 400 ncu --set full --clock-control none --import-source on -k "regex:attn_bwd_vec|box_bwd_win" -s 2 -c 1 -f -o $OUT/bwd_enc_K4 \
     python scripts/prof_driver.py --workload enc --K 4 > $OUT/ncu_bwd.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source off -k "regex:attn_fwd_vec|box_fwd_win" -s 2 -c 1 -f -o $OUT/fwd_enc_K4_uniform \
+timeout 400 ncu --set full --clock-control none --import-source on -k "regex:attn_fwd_vec|box_fwd_win" -s 2 -c 1 -f -o $OUT/fwd_enc_K4_uniform \
     python scripts/prof_driver.py --workload enc --K 4 --dist uniform > $OUT/ncu_fwd_u.log 2>&1
 # the .ncu-rep files have grown past the 64 MiB copy-back limit: digest them here, keep only text
 for r in fwd_enc_K4 bwd_enc_K4 fwd_enc_K4_uniform; do
   if [ -f $OUT/$r.ncu-rep ]; then
     python scripts/ncu_summary.py $OUT/$r.ncu-rep > $OUT/$r.summary.txt 2>&1
-    ncu -i $OUT/$r.ncu-rep --page source --csv > $OUT/$r.source.csv 2>/dev/null
+    ncu -i $OUT/$r.ncu-rep --page source --csv --print-source sass > $OUT/$r.source_sass.csv 2>/dev/null
     ncu -i $OUT/$r.ncu-rep --page details > $OUT/$r.details.txt 2>/dev/null
     rm -f $OUT/$r.ncu-rep
   fi
