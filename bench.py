@@ -565,6 +565,16 @@ def main():
     ach_s = n_samples * (bf + bb) / ((kf_ms + kb_ms) * 1e-3) / 1e9
 
     tr_f, tr_b, tr_src = ncu_traffic()
+    # the second location distribution of SURVEY.md 8(d): uniform-random points (worst-case locality, what the
+    # reference's own tests draw) -- reported beside the headline, same sizes
+    uni = make_sets(dev, 1, seed0=rank_seed(rank) + 100, K=CFG["K"], dist="uniform", B=CFG["B_per_gpu"])
+    uf_ms, ub_ms = kernel_times(ops, uni, 10)
+    uf_ms, ub_ms = kernel_times(ops, uni, 20)
+    del uni
+
+    def dram(tr, ms):      # measured DRAM bytes of the committed ncu capture over the live launch time
+        return None if tr is None else {"GBs": tr / (ms * 1e-3) / 1e9, "frac_of_peak": tr / (ms * 1e-3) / 1e9 / bw_peak}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -575,10 +585,15 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "box_bwd_win_kernel<float,G=8,SUB=8,PPL=2,atomic> (+ grad_value memset)",
                      "achieved": ach_b, "peak": bw_peak, "unit": "GB/s", "frac": ach_b / bw_peak, "traffic": tr_b,
                      "traffic_source": tr_src, "algorithmic_bytes": n_samples * bb,
-                     "peak_source": peak_src, "bytes_per_sample": bb, "ms_per_launch": kb_ms},
+                     "peak_source": peak_src, "bytes_per_sample": bb, "ms_per_launch": kb_ms, "dram": dram(tr_b, kb_ms),
+                     "note": "frac > 1: the no-reuse byte model of SURVEY.md 8(d) counts every corner row as HBM traffic; "
+                             "value (22.8 MB) lives in L1/L2, the measured DRAM traffic is `traffic` (see `dram`), and what "
+                             "binds is instruction issue + gather latency (profiles/README.md)"},
         "roofline_fwd": {"bound": "hbm", "kernel": "box_fwd_win_kernel<float,G=8,SUB=8,PPL=2>", "achieved": ach_f, "peak": bw_peak,
                          "unit": "GB/s", "frac": ach_f / bw_peak, "traffic": tr_f, "algorithmic_bytes": n_samples * bf, "bytes_per_sample": bf,
-                         "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6},
+                         "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6, "dram": dram(tr_f, kf_ms)},
+        "uniform_locations": {"fwd_ms": uf_ms, "bwd_ms": ub_ms, "fwdbwd_Gsamples_per_s": n_samples / (uf_ms + ub_ms) / 1e6,
+                              "note": "same sizes, sampling points drawn uniformly in [0,1)^2 (no spatial structure)"},
         "roofline_step": {"achieved": ach_s, "frac": ach_s / bw_peak, "unit": "GB/s"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,

@@ -73,6 +73,44 @@ def test_argument_validation_without_touching_the_device():
     assert lib.bxr_attn_bwd_workspace_bytes(4, 2, 100, 8, 32, 1) == 256 + 8 * n
 
 
+def test_fused_entry_points_validate_without_touching_the_device():
+    """rows f1-f3 of the scope table: the same status-code behaviour as the four reference-shaped entry points."""
+    from boxer_b200 import _native
+    lib = _native.load()
+    dims = (1, 10, 8, 32, 4, 5, 4)
+    # softmax -> box -> grid -> attention: attn_out is required for a non-empty problem, bad dims are rejected first
+    st = lib.bxr_box_grid_softmax_attn_fwd_f32(None, None, None, None, None, None, None, None, *dims, None, None, None, 0, 0, None)
+    assert st == 1 and b"attn_out" in lib.bxr_last_error_detail()
+    st = lib.bxr_box_grid_softmax_attn_fwd_f32(None, None, None, None, None, None, None, None, 1, 10, 8, 32, 4, -5, 4, None, None, None, 0, 0, None)
+    assert st in (1, 2)
+    st = lib.bxr_box_grid_softmax_attn_bwd_f32(None, None, None, None, None, None, None, None, None, 1, 10, 8, 32, 40, 5, 4,
+                                               None, None, None, None, None, 0, 0, None)
+    assert st == 2                                          # 40 levels > BXR_MAX_LEVELS
+    # instance weights: K must be even, L <= 32, empty problems are fine
+    assert lib.bxr_instance_weights_fwd_f32(None, 10, 4, 3, None, None, None) == 2
+    assert lib.bxr_instance_weights_fwd_f32(None, 10, 33, 4, None, None, None) == 2
+    assert lib.bxr_instance_weights_fwd_f32(None, 0, 4, 4, None, None, None) == 0 and lib.bxr_last_launch_count() == 0
+    assert lib.bxr_instance_weights_fwd_f32(None, 10, 4, 4, None, None, None) == 1
+    assert lib.bxr_instance_weights_bwd_f64(None, None, None, 10, 4, 14, None, None) == 1
+    # value epilogue: element sizes 4 / 2 only
+    assert lib.bxr_value_epilogue(None, 8, None, None, 4, 10, 256, None) == 5
+    assert lib.bxr_value_epilogue(None, 4, None, None, 2, 0, 256, None) == 0
+    assert lib.bxr_value_epilogue(None, 4, None, None, 2, 10, 256, None) == 1
+    # the fused ops' workspace: nothing for the fused kernels' shapes in fp32 forward, the grid otherwise
+    assert lib.bxr_box_grid_attn_workspace_bytes(4, 0, 1, 100, 8, 32, 4, 50, 16, 0) == 0
+    assert lib.bxr_box_grid_attn_workspace_bytes(8, 0, 1, 100, 8, 32, 4, 50, 16, 0) >= 50 * 8 * 4 * 16 * 2 * 8
+
+
+def test_fused_python_wrappers_reject_cpu_tensors_and_bad_shapes():
+    import boxer_b200
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        boxer_b200.ops.instance_weights_forward(torch.zeros(1, 2, 2, 3, 2, 2), 4)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        boxer_b200.ops.value_epilogue(torch.zeros(1, 5, 8), None, torch.bfloat16)
+    with pytest.raises(TypeError):
+        boxer_b200.ops.instance_weights_forward([[1.0]], 4)
+
+
 def test_ops_reject_cpu_tensors_like_the_reference():
     """box_attn.h:53 'Not implemented on the CPU' -- and there is no fallback here either."""
     import boxer_b200
