@@ -58,6 +58,8 @@ def _nvcc() -> str:
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
+    if os.environ.get("BOXER_B200_LIB"):      # an A/B build carries its own -D flags: never rebuild it implicitly
+        return False
     t = os.path.getmtime(LIB_PATH)
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in DEPENDS)
 

@@ -228,13 +228,13 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
 
 template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX>
 int fwd_win(AttnParams& p, cudaStream_t st) {
-    p.units = (int)((p.rows + kWinThreads / G - 1) / (kWinThreads / G));
-    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED, SMAX>, kWinThreads>(p, st, "box_fwd_win_kernel");
+    p.units = (int)((p.rows + kFwdThreads / G - 1) / (kFwdThreads / G));
+    return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED, SMAX>, kFwdThreads>(p, st, "box_fwd_win_kernel");
 }
 template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX>
 int bwd_win(AttnParams& p, cudaStream_t st) {
-    p.units = (int)((p.rows + kWinThreads / G - 1) / (kWinThreads / G));
-    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED, SMAX>, kWinThreads>(p, st, "box_bwd_win_kernel");
+    p.units = (int)((p.rows + kBwdThreads / G - 1) / (kBwdThreads / G));
+    return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED, SMAX>, kBwdThreads>(p, st, "box_bwd_win_kernel");
 }
 
 // (G, SUB, PPL): SUB lanes share a level's points, PPL points per lane; P <= SUB * PPL.

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, BXR_STG_FWD_MINB) box_fwd_stg_kernel
                 LevelBox lbx;
                 if (MODE == 1) lbx = stg_level_box(p, srow, rowc, lmc, b);
                 LanePoint pt[PPL];
-                int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
+                int bx0 = kNoPix, bx1 = -kNoPix, by0 = kNoPix, by1 = -kNoPix;
 #pragma unroll
                 for (int k = 0; k < PPL; ++k) {
                     const int ptn = lact ? slane + k * SUB : p.P;

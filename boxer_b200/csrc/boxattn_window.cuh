@@ -28,14 +28,33 @@
 
 namespace bxr {
 
-// resident CTAs per SM the fp32 window kernels are compiled for (A/B measured on B200, profiles/README.md):
-// forward 3 (<= 80 registers, no spills), backward 4 (<= 64 registers)
+// CTA size and resident CTAs per SM the window kernels are compiled for (A/B measured on B200, profiles/README.md).
+// What matters is warps per SM against the register budget: 65536 / (warps * 32) registers per thread.
+//   forward : 128-thread CTAs, 7 per SM = 28 warps at <= 72 registers (one 4-byte spill).  r01u: 0.1786 -> 0.1757 ms,
+//             uniform locations 0.3627 -> 0.3465 ms against 256 x 3 = 24 warps at 80 registers; 32 warps (64
+//             registers) spill and lose (0.198 ms).
+//   backward: 256-thread CTAs, 4 per SM = 32 warps at 64 registers; 128-thread CTAs cost 3 % there (0.346 -> 0.356 ms),
+//             36 warps (56 registers) spill.
+// The 16-byte-lane bf16 instantiations (8 channels per lane) keep the equivalent of two 256-thread CTAs.
+#ifndef BXR_FWD_THREADS
+#define BXR_FWD_THREADS 128
+#endif
 #ifndef BXR_FWD_MINB
-#define BXR_FWD_MINB 3
+#define BXR_FWD_MINB 7
+#endif
+#ifndef BXR_BWD_THREADS
+#define BXR_BWD_THREADS 256
 #endif
 #ifndef BXR_BWD_MINB
 #define BXR_BWD_MINB 4
 #endif
+constexpr int kFwdThreads = BXR_FWD_THREADS, kFwdMinB = BXR_FWD_MINB;
+// the 72-register budget holds for the location-taking kernels with up to 2 points per lane (ptxas: 4 bytes of
+// spill); the fused-grid / softmax variants and 4 points per lane keep the 80-register budget (24 warps)
+constexpr int fwd_min_blocks(int vec, int ppl, bool fused) {
+    return vec > 4 ? 2 * (kThreads / kFwdThreads) : ((fused || ppl > 2) ? 3 * (kThreads / kFwdThreads) : kFwdMinB);
+}
+constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 // unroll factors of the per-point fallback loops: the walk is a chain of dependent gathers, unrolling lets the
 // compiler request the corner rows of several points before the first is used (A/B r01s: forward 1 -> 8:
 // 0.1846 -> 0.1794 ms, uniform 0.382 -> 0.362 ms; backward 1 -> 4: 0.365 -> 0.350 ms, 8 is worse there)
@@ -46,14 +65,6 @@ namespace bxr {
 #define BXR_FB_UNROLL_BWD 4
 #endif
 
-// CTA size of the window kernels: a work unit is one CTA's worth of rows, and with ~12 units per CTA the last
-// unit's quantum is the tail of the launch -- smaller CTAs, smaller quantum (A/B: profiles/README.md)
-#ifndef BXR_WIN_THREADS
-#define BXR_WIN_THREADS 256
-#endif
-constexpr int kWinThreads = BXR_WIN_THREADS;
-constexpr int kWinCtaScale = kThreads / kWinThreads;      // resident-CTA targets below are stated for 256 threads
-
 // Work units are dealt round-robin from the LAST one down: in BoxeR's encoder the trailing queries belong to the
 // coarse levels, whose rows cost several times more (wide footprints -> per-point walk); starting with them leaves
 // the cheap units for the tail of the launch (A/B r01q: forward 0.1875 -> 0.1844 ms; harmless for other inputs).
@@ -62,6 +73,10 @@ constexpr int kWinCtaScale = kThreads / kWinThreads;      // resident-CTA target
 #endif
 constexpr int kFbUnroll = BXR_FB_UNROLL;
 constexpr int kFbUnrollBwd = BXR_FB_UNROLL_BWD;
+// "no pixel touched yet" sentinel of the range reductions: with +-kNoPix in both ends the extent
+// max - min + 1 of an empty range is a large negative number that still fits an int (+-INT_MAX wrapped
+// around to 3, which sent rows without any in-range point through a 3 x 3 window of zeros)
+constexpr int kNoPix = 0x3fffffff;
 constexpr int kWinSide = 8;
 constexpr int kWinSlots = kWinSide * kWinSide;
 // per-group pitch of a window in 32-bit words: 64 slots + 4 words of skew, so that the 16-byte
@@ -262,12 +277,12 @@ struct SubWin {
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
 // SMAX (with FUSED): `w0` holds logits; the softmax over the row's L*P points is taken here and written to attn_out.
 template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX = false>
-__global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_FWD_MINB) * kWinCtaScale) box_fwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PPL, FUSED)) box_fwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax prologue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
-    constexpr int GROUPS = kWinThreads / G;
+    constexpr int GROUPS = kFwdThreads / G;
     constexpr int LPP = GEO::LPP, CAP = GEO::CAP;
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_F
             const int lmc = lm < p.L ? lm : 0;
             const int mh = lv.h[lmc], mw = lv.w[lmc];
             LanePoint pt[PPL];
-            int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
+            int bx0 = kNoPix, bx1 = -kNoPix, by0 = kNoPix, by1 = -kNoPix;
             float S = 0.f;
             LevelBox lbx;
             if constexpr (FUSED) lbx = load_level_box(p, row * p.L + lmc, b, lmc);
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_F
             me.nx = min(smax<SUB>(bx1, kFullMask), mw - 1) - me.X0 + 1;
             me.ny = min(smax<SUB>(by1, kFullMask), mh - 1) - me.Y0 + 1;
             S = ssum<SUB>(S, kFullMask);
-            const int nq = me.nx * me.ny;
+            const int nq = (me.nx > 0 && me.ny > 0) ? me.nx * me.ny : 0;
             // non-finite weights (S is NaN/inf) take the float path so that they propagate
             me.mode = (me.nx <= 0 || me.ny <= 0 || S == 0.f) ? 0 : ((nq <= CAP && S <= 3.0e38f) ? 1 : 2);
             me.ke = fixed_scale_exp(S);
@@ -498,12 +513,12 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
 // SMAX (with FUSED): `w0` holds the softmax weights the forward wrote; the weight gradients are chained through
 // the softmax before they leave the kernel:  grad_logit = w * (grad_w - sum_row(w * grad_w)).
 template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX = false>
-__global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_BWD_MINB) * kWinCtaScale) box_bwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThreads / kBwdThreads) : kBwdMinB) box_bwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax epilogue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
     constexpr int VEC = V::VEC;
-    constexpr int GROUPS = kWinThreads / G;
+    constexpr int GROUPS = kBwdThreads / G;
     constexpr int LPP = GEO::LPP, CAP = GEO::CAP;
     constexpr bool DET = sizeof(ACC) == 8;
     __shared__ LevelTable lv;
@@ -552,7 +567,7 @@ __global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_B
             const int mh = lv.h[lmc], mw = lv.w[lmc];
             LanePoint pt[PPL];
             float g_a[PPL], g_x[PPL], g_y[PPL];     // this lane's results for its own points
-            int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
+            int bx0 = kNoPix, bx1 = -kNoPix, by0 = kNoPix, by1 = -kNoPix;
             float S = 0.f;
             LevelBox lbx;
             if constexpr (FUSED) lbx = load_level_box(p, row * p.L + lmc, b, lmc);
@@ -573,7 +588,7 @@ __global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_B
             me.nx = min(smax<SUB>(bx1, kFullMask), mw - 1) - me.X0 + 1;
             me.ny = min(smax<SUB>(by1, kFullMask), mh - 1) - me.Y0 + 1;
             S = ssum<SUB>(S, kFullMask);
-            const int nq = me.nx * me.ny;
+            const int nq = (me.nx > 0 && me.ny > 0) ? me.nx * me.ny : 0;
             me.mode = (me.nx <= 0 || me.ny <= 0) ? 0 : ((nq <= CAP && S <= 3.0e38f) ? 1 : 2);
             me.ke = fixed_scale_exp(fmaxf(S, 1e-30f));
 
@@ -634,9 +649,9 @@ __global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_B
                     int ix = 0;
                     for (int q = 0; q < wq_n; q += 4) {
                         const int4 wq = *reinterpret_cast<const int4*>(cwin + q);
-                        const float4 tq = *reinterpret_cast<const float4*>(cdot + q);
                         const int wi[4] = {wq.x, wq.y, wq.z, wq.w};
-                        const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                        const float4 tq = *reinterpret_cast<const float4*>(cdot + q);
+                        const bool tv[4] = {tq.x != 0.f, tq.y != 0.f, tq.z != 0.f, tq.w != 0.f};
                         unsigned offs[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -647,7 +662,7 @@ __global__ void __launch_bounds__(kWinThreads, ((Vec16<TV>::VEC > 4) ? 2 : BXR_B
                         float v[4][VEC];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (tv[j] != 0.f) {        // slots past nq were zeroed and never flagged
+                            if (tv[j]) {               // slots past nq were zeroed and never flagged
                                 V::load16(value16, offs[j], v[j]);
                             } else {
 #pragma unroll
