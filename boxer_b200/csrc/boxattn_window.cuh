@@ -49,10 +49,12 @@ namespace bxr {
 #define BXR_BWD_MINB 4
 #endif
 constexpr int kFwdThreads = BXR_FWD_THREADS, kFwdMinB = BXR_FWD_MINB;
-// the 72-register budget holds for the location-taking kernels with up to 2 points per lane (ptxas: 4 bytes of
-// spill); the fused-grid / softmax variants and 4 points per lane keep the 80-register budget (24 warps)
-constexpr int fwd_min_blocks(int vec, int ppl, bool fused) {
-    return vec > 4 ? 2 * (kThreads / kFwdThreads) : ((fused || ppl > 2) ? 3 * (kThreads / kFwdThreads) : kFwdMinB);
+// the 72-register budget holds for the fp32 location-taking kernels with up to 2 points per lane (ptxas: 4 bytes of
+// spill); the fused-grid / softmax variants, 4 points per lane and the bf16 kernels (unpacking registers; r01x:
+// bf16 forward 3-6 % slower at 72) keep the 80-register budget (24 warps)
+constexpr int fwd_min_blocks(int vec, int ppl, bool fused, bool fp32) {
+    return vec > 4 ? 2 * (kThreads / kFwdThreads)
+                   : ((fused || ppl > 2 || !fp32) ? 3 * (kThreads / kFwdThreads) : kFwdMinB);
 }
 constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 // unroll factors of the per-point fallback loops: the walk is a chain of dependent gathers, unrolling lets the
@@ -277,7 +279,7 @@ struct SubWin {
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
 // SMAX (with FUSED): `w0` holds logits; the softmax over the row's L*P points is taken here and written to attn_out.
 template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX = false>
-__global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PPL, FUSED)) box_fwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PPL, FUSED, std::is_same<TV, float>::value)) box_fwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax prologue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
