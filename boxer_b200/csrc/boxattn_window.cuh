@@ -57,6 +57,17 @@ constexpr int fwd_min_blocks(int vec, int ppl, bool fused, bool fp32) {
                    : ((fused || ppl > 2 || !fp32) ? 3 * (kThreads / kFwdThreads) : kFwdMinB);
 }
 constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
+// Forward window walk from a slot table: after the scatter, the lanes of the level turn the dense window into
+// (pixel offset, float weight) pairs, one lane per slot, and the walk reads two pairs per 16-byte shared load --
+// the per-slot index arithmetic (row wrap, int -> float, scaling: 9 of the 16 instructions a slot costs) is done
+// once per slot instead of once per slot and lane.  Measured (r02a, K=4 encoder forward): bf16 0.1988 -> 0.1858 ms,
+// fp32 at 28 warps / 72 registers 0.1786 -> 0.1865 ms (the table adds a shared-memory round trip to every pass and
+// the fp32 kernel waits on latency, not on issue slots).  BXR_FWD_TAB: 0 off, 1 all types, 2 all but fp32 (default).
+#ifndef BXR_FWD_TAB
+#define BXR_FWD_TAB 2
+#endif
+template <typename TV>
+struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD_TAB == 2 && !std::is_same<TV, float>::value); };
 // unroll factors of the per-point fallback loops: the walk is a chain of dependent gathers, unrolling lets the
 // compiler request the corner rows of several points before the first is used (A/B r01s: forward 1 -> 8:
 // 0.1846 -> 0.1794 ms, uniform 0.382 -> 0.362 ms; backward 1 -> 4: 0.365 -> 0.350 ms, 8 is worse there)
@@ -84,6 +95,8 @@ constexpr int kWinSlots = kWinSide * kWinSide;
 // per-group pitch of a window in 32-bit words: 64 slots + 4 words of skew, so that the 16-byte
 // row reads of the 4 (G=8) or 8 (G=4) groups of a warp fall into different banks
 constexpr int kWinPitch = kWinSlots + 4;
+// slot table: 8-byte entries, pitch 64 + 2 entries (528 bytes: a multiple of 16, and the groups of a warp are 4 banks apart)
+constexpr int kTabPitch = kWinSlots + 2;
 
 // Pixel weights are accumulated in the shared-memory window as 32-bit fixed point with a per
 // (row, level) power-of-two scale: integer atomics are single instructions (a float atomicAdd on
@@ -288,6 +301,8 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
     constexpr int LPP = GEO::LPP, CAP = GEO::CAP;
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];
+    constexpr bool TAB = FwdSlotTable<TV>::value;
+    __shared__ __align__(16) uint2 s_tab[TAB ? GROUPS * kTabPitch : 2];
     load_levels(lv, p);
 
     const int lane = threadIdx.x % G;
@@ -296,6 +311,8 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
     const unsigned gm = group_mask<G>();
     int* gwin = s_win + gid * kWinPitch;
     int* win = gwin + sub * CAP;
+    uint2* gtab = s_tab + (TAB ? gid * kTabPitch : 0);
+    uint2* tab = gtab + (TAB ? sub * CAP : 0);
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in lane chunks (VEC elements)
     const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -384,6 +401,23 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                 }
             }
             __syncwarp();
+            // ---- B': one lane per slot: dense slot s = (y, x) -> (value offset relative to the row's base, weight)
+            if (TAB && me.mode == 1) {
+                const float inv_scale = pow2f(-me.ke);
+                // s / nx for s < 64, nx <= 64 as a multiply-shift: rcp = floor(65536 / nx) + 1
+                const unsigned rcp = (unsigned)__float2int_rz(__fdividef(65536.f, (float)me.nx)) + 1u;
+                const unsigned tbase = ((unsigned)lv.start[lmc] + (unsigned)(me.Y0 * mw + me.X0)) * HDV;
+                const unsigned trow = (unsigned)mw * HDV;
+                const int nq4 = (nq + 3) & ~3;
+#pragma unroll 2
+                for (int ts = slane; ts < nq4; ts += SUB) {
+                    const unsigned y = ((unsigned)ts * rcp) >> 16;
+                    const unsigned x = (unsigned)ts - y * (unsigned)me.nx;
+                    const float wv = (float)win[ts] * inv_scale;            // slots past nq were zeroed: weight 0
+                    tab[ts] = make_uint2(tbase + y * trow + x * HDV, __float_as_uint(wv));
+                }
+            }
+            if constexpr (TAB) __syncwarp();
 
             // ---- C: all G lanes walk the window(s) of this pass
 #pragma unroll
@@ -401,7 +435,32 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                 const int l = l0 + sl;
                 const int lh = lv.h[l], lw = lv.w[l];
                 const unsigned vlev = vrow + (unsigned)lv.start[l] * HDV;
-                if (w.mode == 1) {
+                if (TAB && w.mode == 1) {
+                    // one row load per unique pixel, four table entries (two 16-byte shared loads) at a time
+                    const uint2* ct = gtab + sl * CAP;
+                    const int wq_n = w.nx * w.ny;
+                    // per-lane base pointer in registers: the table offsets are the same for all lanes of the group
+                    const typename V::Raw* vlane = static_cast<const typename V::Raw*>(value16) + vrow;
+                    asm volatile("" : "+l"(vlane));      // keep it a register pair: one IMAD.WIDE per load, no re-derivation
+#pragma unroll 2
+                    for (int q = 0; q < wq_n; q += 4) {
+                        const uint4 t0 = *reinterpret_cast<const uint4*>(ct + q);
+                        const uint4 t1 = *reinterpret_cast<const uint4*>(ct + q + 2);
+                        const unsigned to[4] = {t0.x, t0.z, t1.x, t1.z};
+                        const float tw[4] = {__uint_as_float(t0.y), __uint_as_float(t0.w), __uint_as_float(t1.y), __uint_as_float(t1.w)};
+                        float v[4][VEC];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (tw[j] != 0.f) V::load16(vlane, to[j], v[j]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (tw[j] != 0.f) {
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) acc[i] += tw[j] * v[j][i];
+                            }
+                        }
+                    }
+                } else if (w.mode == 1) {
                     // one row load per unique pixel, four window slots at a time; the pixel index is
                     // advanced incrementally (no division by nx)
                     const int* cw = gwin + sl * CAP;

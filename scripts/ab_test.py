@@ -20,4 +20,9 @@ for name, w in (("K4_box", W.coco_encoder(K=4, device="cuda")), ("K4_uni", W.coc
     go = torch.randn(1, w.value.shape[1], 256, device="cuda")
     a = (w.value, w.shapes, w.level_start, w.loc, w.weights[0])
     res[name] = (round(time_call(lambda: ops.box_attn_forward(*a, 64)), 4), round(time_call(lambda: ops.box_attn_backward(*a, go, 64)), 4))
+w = W.coco_encoder(K=4, device="cuda")
+vb = w.value.to(torch.bfloat16)
+gb = torch.randn(1, vb.shape[1], 256, device="cuda", dtype=torch.bfloat16)
+ab = (vb, w.shapes, w.level_start, w.loc, w.weights[0])
+res["K4_box_bf16"] = (round(time_call(lambda: ops.box_attn_forward(*ab, 64)), 4), round(time_call(lambda: ops.box_attn_backward(*ab, gb, 64)), 4))
 print(json.dumps(res))
