@@ -55,6 +55,16 @@ def ncu_traffic():
         return None, None, None
 
 
+def ncu_issue():
+    """Issue-slot utilisation (%) of the two kernels in the committed ncu capture: the resource that actually binds."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get("fwd_issue_active_pct"), t.get("bwd_issue_active_pct")
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -565,6 +575,7 @@ def main():
     ach_s = n_samples * (bf + bb) / ((kf_ms + kb_ms) * 1e-3) / 1e9
 
     tr_f, tr_b, tr_src = ncu_traffic()
+    is_f, is_b = ncu_issue()
     # the second location distribution of SURVEY.md 8(d): uniform-random points (worst-case locality, what the
     # reference's own tests draw) -- reported beside the headline, same sizes
     uni = make_sets(dev, 1, seed0=rank_seed(rank) + 100, K=CFG["K"], dist="uniform", B=CFG["B_per_gpu"])
@@ -586,12 +597,13 @@ def main():
                      "achieved": ach_b, "peak": bw_peak, "unit": "GB/s", "frac": ach_b / bw_peak, "traffic": tr_b,
                      "traffic_source": tr_src, "algorithmic_bytes": n_samples * bb,
                      "peak_source": peak_src, "bytes_per_sample": bb, "ms_per_launch": kb_ms, "dram": dram(tr_b, kb_ms),
+                     "issue_active_pct_ncu": is_b,
                      "note": "frac > 1: the no-reuse byte model of SURVEY.md 8(d) counts every corner row as HBM traffic; "
                              "value (22.8 MB) lives in L1/L2, the measured DRAM traffic is `traffic` (see `dram`), and what "
                              "binds is instruction issue + gather latency (profiles/README.md)"},
         "roofline_fwd": {"bound": "hbm", "kernel": "box_fwd_win_kernel<float,G=8,SUB=8,PPL=2>", "achieved": ach_f, "peak": bw_peak,
                          "unit": "GB/s", "frac": ach_f / bw_peak, "traffic": tr_f, "algorithmic_bytes": n_samples * bf, "bytes_per_sample": bf,
-                         "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6, "dram": dram(tr_f, kf_ms)},
+                         "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6, "dram": dram(tr_f, kf_ms), "issue_active_pct_ncu": is_f},
         "uniform_locations": {"fwd_ms": uf_ms, "bwd_ms": ub_ms, "fwdbwd_Gsamples_per_s": n_samples / (uf_ms + ub_ms) / 1e6,
                               "note": "same sizes, sampling points drawn uniformly in [0,1)^2 (no spatial structure)"},
         "roofline_step": {"achieved": ach_s, "frac": ach_s / bw_peak, "unit": "GB/s"},
