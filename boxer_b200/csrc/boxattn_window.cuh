@@ -52,9 +52,15 @@ constexpr int kFwdThreads = BXR_FWD_THREADS, kFwdMinB = BXR_FWD_MINB;
 // the 72-register budget holds for the fp32 location-taking kernels with up to 2 points per lane (ptxas: 4 bytes of
 // spill); the fused-grid / softmax variants, 4 points per lane and the bf16 kernels (unpacking registers; r01x:
 // bf16 forward 3-6 % slower at 72) keep the 80-register budget (24 warps)
-constexpr int fwd_min_blocks(int vec, int ppl, bool fused, bool fp32) {
+// BXR_FWD_MINB_LPP2 (next-round A/B hook, default = BXR_FWD_MINB): resident CTAs of the two-levels-per-pass
+// kernels (2 x 2 grids), which measured 2 % faster at 6 x 128 threads / 80 registers (r02b: 0.0860 vs 0.0885 ms)
+#ifndef BXR_FWD_MINB_LPP2
+#define BXR_FWD_MINB_LPP2 BXR_FWD_MINB
+#endif
+constexpr int fwd_min_blocks(int vec, int ppl, bool fused, bool fp32, bool two_levels) {
     return vec > 4 ? 2 * (kThreads / kFwdThreads)
-                   : ((fused || ppl > 2 || !fp32) ? 3 * (kThreads / kFwdThreads) : kFwdMinB);
+                   : ((fused || ppl > 2 || !fp32) ? 3 * (kThreads / kFwdThreads)
+                                                  : (two_levels ? BXR_FWD_MINB_LPP2 : kFwdMinB));
 }
 constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 // Forward window walk from a slot table: after the scatter, the lanes of the level turn the dense window into
@@ -68,6 +74,12 @@ constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 #endif
 template <typename TV>
 struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD_TAB == 2 && !std::is_same<TV, float>::value); };
+// BXR_BASE_REGPAIR (next-round A/B hook, default 0): gather through a per-lane base pointer kept as an opaque
+// register pair, offsets relative to it -- one IMAD.WIDE per load; otherwise the compiler re-loads the tensor
+// base from the constant bank (LDC.64) in front of every load (seen in SASS, boxattn_window.cuh forward walk)
+#ifndef BXR_BASE_REGPAIR
+#define BXR_BASE_REGPAIR 0
+#endif
 // unroll factors of the per-point fallback loops: the walk is a chain of dependent gathers, unrolling lets the
 // compiler request the corner rows of several points before the first is used (A/B r01s: forward 1 -> 8:
 // 0.1846 -> 0.1794 ms, uniform 0.382 -> 0.362 ms; backward 1 -> 4: 0.365 -> 0.350 ms, 8 is worse there)
@@ -292,7 +304,7 @@ struct SubWin {
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
 // SMAX (with FUSED): `w0` holds logits; the softmax over the row's L*P points is taken here and written to attn_out.
 template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX = false>
-__global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PPL, FUSED, std::is_same<TV, float>::value)) box_fwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PPL, FUSED, std::is_same<TV, float>::value, SUB < G)) box_fwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax prologue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
@@ -434,7 +446,14 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
                 const int lh = lv.h[l], lw = lv.w[l];
+#if BXR_BASE_REGPAIR
+                const typename V::Raw* vbase = static_cast<const typename V::Raw*>(value16) + vrow;
+                asm volatile("" : "+l"(vbase));
+                const unsigned vlev = (unsigned)lv.start[l] * HDV;
+#else
+                const void* vbase = value16;
                 const unsigned vlev = vrow + (unsigned)lv.start[l] * HDV;
+#endif
                 if (TAB && w.mode == 1) {
                     // one row load per unique pixel, four table entries (two 16-byte shared loads) at a time
                     const uint2* ct = gtab + sl * CAP;
@@ -483,7 +502,7 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                         float v[4][VEC];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (wi[j] != 0) V::load16(value16, offs[j], v[j]);   // slots past nq were zeroed and never written
+                            if (wi[j] != 0) V::load16(vbase, offs[j], v[j]);   // slots past nq were zeroed and never written
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (wi[j] != 0) {
@@ -514,7 +533,7 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                             float v[4][VEC];
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
-                                if (ok[c]) V::load16(value16, c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u), v[c]);
+                                if (ok[c]) V::load16(vbase, c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u), v[c]);
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
                                 if (ok[c]) {
@@ -697,7 +716,16 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
                 const int lh = lv.h[l], lw = lv.w[l];
+#if BXR_BASE_REGPAIR
+                const typename V::Raw* vptr = static_cast<const typename V::Raw*>(value16) + vbase;
+                ACC* gptr = gacc + (size_t)vbase * VEC;
+                asm volatile("" : "+l"(vptr), "+l"(gptr));
+                const unsigned lbase = (unsigned)lv.start[l] * HDV;
+#else
+                const void* vptr = value16;
+                ACC* gptr = gacc;
                 const unsigned lbase = vbase + (unsigned)lv.start[l] * HDV;
+#endif
                 if (w.mode == 1) {
                     // per unique pixel, four window slots at a time:
                     // value row -> scatter W*go into grad_value, d = <go, v> by transpose reduction
@@ -724,7 +752,7 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (tv[j]) {               // slots past nq were zeroed and never flagged
-                                V::load16(value16, offs[j], v[j]);
+                                V::load16(vptr, offs[j], v[j]);
                             } else {
 #pragma unroll
                                 for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
@@ -737,7 +765,7 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
                             dsum[j] = t;
-                            if (wi[j] != 0) scatter_row<ACC, VEC>(gacc + (size_t)offs[j] * VEC, go, (float)wi[j] * inv_scale, dscale);
+                            if (wi[j] != 0) scatter_row<ACC, VEC>(gptr + (size_t)offs[j] * VEC, go, (float)wi[j] * inv_scale, dscale);
                         }
                         float total;
                         const int mine = reduce4<G>(dsum, total, lane, gm);
@@ -769,10 +797,10 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                                 if (ok[c]) {
                                     const unsigned off = c00 + ((c & 1) ? HDV : 0u) + ((c & 2) ? (unsigned)lw * HDV : 0u);
                                     float v[VEC];
-                                    V::load16(value16, off, v);
+                                    V::load16(vptr, off, v);
 #pragma unroll
                                     for (int i = 0; i < VEC; ++i) t += go[i] * v[i];
-                                    scatter_row<ACC, VEC>(gacc + (size_t)off * VEC, go, cw[c] * aw, dscale);
+                                    scatter_row<ACC, VEC>(gptr + (size_t)off * VEC, go, cw[c] * aw, dscale);
                                 }
                                 d[c] = t;
                             }
