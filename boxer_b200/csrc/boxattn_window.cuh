@@ -74,6 +74,14 @@ constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 #endif
 template <typename TV>
 struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD_TAB == 2 && !std::is_same<TV, float>::value); };
+// BXR_BWD_TAB (next-round A/B hook, default 0; written without a GPU at hand -- run the window tests on it first):
+// the backward walk from a slot table like the bf16 forward's.  One lane per slot writes (offset relative to the
+// lane's base pointers, float weight) after the scatter; an untouched slot carries a NaN weight.  The walk then
+// needs no row-wrap arithmetic, no flag read, no int -> float scaling per lane, and no group barrier before the
+// d totals overwrite the flag window (the flags are consumed when the table is built).
+#ifndef BXR_BWD_TAB
+#define BXR_BWD_TAB 0
+#endif
 // BXR_BASE_REGPAIR (next-round A/B hook, default 0): gather through a per-lane base pointer kept as an opaque
 // register pair, offsets relative to it -- one IMAD.WIDE per load; otherwise the compiler re-loads the tensor
 // base from the constant bank (LDC.64) in front of every load (seen in SASS, boxattn_window.cuh forward walk)
@@ -604,6 +612,8 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];     // pixel weights W[pix], fixed point
     __shared__ __align__(16) float s_dot[GROUPS * kWinPitch];   // "touched" flag, then d[pix] = <grad_out, value[pix]>
+    constexpr bool TABB = (BXR_BWD_TAB != 0) && G >= 8;     // G = 4: 64 groups per CTA, the table would not fit 48 KB
+    __shared__ __align__(16) uint2 s_tab[TABB ? GROUPS * kTabPitch : 2];
     load_levels(lv, p);
 
     const int lane = threadIdx.x % G;
@@ -614,6 +624,8 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     float* gdot = s_dot + gid * kWinPitch;
     int* win = gwin + sub * CAP;
     float* dot = gdot + sub * CAP;
+    uint2* gtab = s_tab + (TABB ? gid * kTabPitch : 0);
+    uint2* tab = gtab + (TABB ? sub * CAP : 0);
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in lane chunks (VEC elements)
     const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -700,6 +712,22 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                 }
             }
             __syncwarp();
+            // B': one lane per slot: (offset from the lane's base pointers, weight; NaN = nobody touched this pixel)
+            if (TABB && me.mode == 1) {
+                const float inv_scale = pow2f(-me.ke);
+                const unsigned rcp = (unsigned)__float2int_rz(__fdividef(65536.f, (float)me.nx)) + 1u;   // s / nx, s < 64
+                const unsigned tbase = ((unsigned)lv.start[lmc] + (unsigned)(me.Y0 * mw + me.X0)) * HDV;
+                const unsigned trow = (unsigned)mw * HDV;
+                const int nq4 = (nq + 3) & ~3;
+#pragma unroll 2
+                for (int ts = slane; ts < nq4; ts += SUB) {
+                    const unsigned y = ((unsigned)ts * rcp) >> 16;
+                    const unsigned x = (unsigned)ts - y * (unsigned)me.nx;
+                    const float wv = dot[ts] != 0.f ? (float)win[ts] * inv_scale : __int_as_float(0x7fc00000);
+                    tab[ts] = make_uint2(tbase + y * trow + x * HDV, __float_as_uint(wv));
+                }
+            }
+            if constexpr (TABB) __syncwarp();
 
             // C: all G lanes walk the window(s) of this pass
 #pragma unroll
@@ -726,7 +754,43 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                 ACC* gptr = gacc;
                 const unsigned lbase = vbase + (unsigned)lv.start[l] * HDV;
 #endif
-                if (w.mode == 1) {
+                if (TABB && w.mode == 1) {
+                    const uint2* ct = gtab + sl * CAP;
+                    float* cdot = gdot + sl * CAP;
+                    const int wq_n = w.nx * w.ny;
+                    // lane base pointers as opaque register pairs; the table offsets are shared by the group's lanes
+                    const typename V::Raw* tvp = static_cast<const typename V::Raw*>(value16) + vbase;
+                    ACC* tgp = gacc + (size_t)vbase * VEC;
+                    asm volatile("" : "+l"(tvp), "+l"(tgp));
+                    for (int q = 0; q < wq_n; q += 4) {
+                        const uint4 t0 = *reinterpret_cast<const uint4*>(ct + q);
+                        const uint4 t1 = *reinterpret_cast<const uint4*>(ct + q + 2);
+                        const unsigned to[4] = {t0.x, t0.z, t1.x, t1.z};
+                        const float tw[4] = {__uint_as_float(t0.y), __uint_as_float(t0.w), __uint_as_float(t1.y), __uint_as_float(t1.w)};
+                        float v[4][VEC];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (tw[j] == tw[j]) {      // touched (an untouched slot carries NaN)
+                                V::load16(tvp, to[j], v[j]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
+                            }
+                        }
+                        float dsum[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
+                            dsum[j] = t;
+                            if (fabsf(tw[j]) > 0.f) scatter_row<ACC, VEC>(tgp + (size_t)to[j] * VEC, go, tw[j], dscale);   // false for NaN
+                        }
+                        float total;
+                        const int mine = reduce4<G>(dsum, total, lane, gm);
+                        cdot[q + mine] = total;                                // lanes sharing an index write the same value
+                    }
+                } else if (w.mode == 1) {
                     // per unique pixel, four window slots at a time:
                     // value row -> scatter W*go into grad_value, d = <go, v> by transpose reduction
                     const int* cwin = gwin + sl * CAP;
