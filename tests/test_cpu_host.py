@@ -253,3 +253,23 @@ def test_module_init_matches_reference_init():
     assert torch.allclose(r.kernel_indices.abs(), torch.full((4, 2), 0.25))      # /2, not /K (box_attention.py:291)
     r3 = boxer_b200.Box3dAttention(256, 2, 8, with_rotation=False, kernel_size=3)
     assert torch.allclose(r3.kernel_indices.abs().max(), torch.tensor(0.5))
+
+
+def test_slot_table_index_arithmetic():
+    """The slot-table walks (boxattn_window.cuh, phase B') split a dense window slot s < 64 into (row, column) with a
+    multiply-shift instead of a division: y = (s * rcp) >> 16 with rcp = floor(q) + 1, q ~ 65536 / nx from the fast
+    (2 ulp) float division.  Host restatement of that identity, including the approximate quotient landing on
+    either side of the exact one, and of the empty-range sentinel arithmetic (kNoPix = 2^30 - 1 stays inside int32)."""
+    import numpy as np
+    for nx in range(1, 65):
+        q = np.float32(65536.0) / np.float32(nx)
+        for qq in (np.nextafter(q, np.float32(0)), q, np.nextafter(q, np.float32(1e9)),
+                   np.nextafter(np.nextafter(q, np.float32(1e9)), np.float32(1e9)),
+                   np.nextafter(np.nextafter(q, np.float32(0)), np.float32(0))):
+            rcp = int(np.floor(qq)) + 1
+            for s in range(64):
+                y = (s * rcp) >> 16
+                assert y == s // nx and s - y * nx == s % nx, (nx, s, rcp)
+    k = 0x3FFFFFFF
+    for hi in (1, 10 ** 6):                      # extent of an empty range: max - min + 1 with the clamps applied
+        assert -(2 ** 31) <= min(-k, hi - 1) - max(k, 0) + 1 < 0
