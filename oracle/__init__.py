@@ -4,7 +4,7 @@ Nothing under ``oracle/`` is part of the product.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import it, and only as the checker (or as the timed
 CPU baseline) -- never as the thing shipped.  ``boxer_b200`` must not import
-this package; ``tests/test_layout.py`` enforces that.
+this package; ``tests/test_cpu_host.py::test_product_never_imports_the_oracle`` enforces that.
 
 Two independent restatements live here:
 
