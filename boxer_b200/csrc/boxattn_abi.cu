@@ -86,8 +86,13 @@ int sm_count() {
 
 template <void (*K)(const AttnParams), int THREADS = kThreads>
 int ctas_per_sm() {
-    static int occ = 0;   // immutable once set; a benign race only recomputes the same number
-    if (occ == 0) {
+    // per device: the occupancy answer and the carve-out hint belong to the (kernel, device) pair -- a second GPU
+    // driven from the same process gets its own query and its own hint.  Entries are immutable once set; a benign
+    // race only recomputes the same number.
+    static int occ[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (occ[dev] == 0) {
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, THREADS, 0) != cudaSuccess || n <= 0) n = 1;
 #if BXR_TRIM_CARVEOUT
@@ -102,9 +107,9 @@ int ctas_per_sm() {
             cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }
 #endif
-        occ = n;
+        occ[dev] = n;
     }
-    return occ;
+    return occ[dev];
 }
 
 template <void (*K)(const AttnParams), int THREADS = kThreads>

@@ -310,6 +310,10 @@ def _aligned16(t):
     return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
 
 
+def _aligned16_opt(t):
+    return None if t is None else _aligned16(t)
+
+
 def box_grid_attn_forward(value, spatial_shapes, level_start_index, boxes, angles, valid_ratios, kernel_indices,
                           attn_weight, im2col_step=64, softmax=False):
     """out = box_attn_forward(value, ..., grid(boxes, angles, valid_ratios, kernel_indices), attn_weight) with the
@@ -323,7 +327,10 @@ def box_grid_attn_forward(value, spatial_shapes, level_start_index, boxes, angle
     suf, _ = _dtypes(value, boxes, (attn_weight, kernel_indices, *opt))
     _step_check(B, im2col_step)
     lib = _native.load()
+    # the workspace query below assumes the fused kernels' alignment requirements hold (boxattn_abi.cu fused_forward):
+    # repair odd-offset views of the small operands here instead of sizing a location workspace for every call
     value, boxes = _aligned16(value), _aligned16(boxes)
+    kernel_indices, valid_ratios, angles = _aligned16(kernel_indices), _aligned16_opt(valid_ratios), _aligned16_opt(angles)
     out = torch.empty((B, Nq, H * D), dtype=value.dtype, device=value.device)
     attn_out = torch.empty_like(attn_weight) if softmax else None
     with _on_device(value.device):
@@ -358,6 +365,7 @@ def box_grid_attn_backward(value, spatial_shapes, level_start_index, boxes, angl
     lib = _native.load()
     flags = (FLAG_DETERMINISTIC if deterministic() else 0) | _PATH_FLAGS
     value, boxes, grad_output = _aligned16(value), _aligned16(boxes), _aligned16(grad_output)
+    kernel_indices, valid_ratios, angles = _aligned16(kernel_indices), _aligned16_opt(valid_ratios), _aligned16_opt(angles)
     grad_value = torch.empty_like(value)
     grad_boxes = torch.empty_like(boxes)
     grad_angles = torch.empty_like(angles) if angles is not None else None

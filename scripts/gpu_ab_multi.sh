@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B several builds of the library in one gpurun call: scripts/ab_test.py with each, two interleaved rounds.
+# A/B several builds of the library in one gpurun call: scripts/ab_bench.py with each, two interleaved rounds.
 # usage: gpurun --timeout 600 -- 'bash scripts/gpu_ab_multi.sh <tag> <lib> [<lib> ...]'   ("default" = the in-tree build)
 TAG=$1; shift
 OUT=gpurun_out/$TAG
@@ -8,9 +8,9 @@ for round in 1 2; do
   for lib in "$@"; do
     name=$(basename $lib .so)
     if [ "$lib" = "default" ]; then
-      python scripts/ab_test.py > $OUT/${name}_$round.json 2>> $OUT/err.log
+      python scripts/ab_bench.py > $OUT/${name}_$round.json 2>> $OUT/err.log
     else
-      BOXER_B200_LIB=$lib python scripts/ab_test.py > $OUT/${name}_$round.json 2>> $OUT/err.log
+      BOXER_B200_LIB=$lib python scripts/ab_bench.py > $OUT/${name}_$round.json 2>> $OUT/err.log
     fi
     echo "$name $round: $(cat $OUT/${name}_$round.json)"
   done
