@@ -13,6 +13,12 @@ Location distributions:
   ``_where_to_attend`` (box_attention.py:196-214).  Decoder / mask head: random boxes.
 * ``"uniform"`` -- every sample point U[0,1)^2 independently (what the reference unit tests
   draw; worst case for locality).
+* ``"trained"`` -- trained-like encoder boxes: what ``"box"`` becomes once ``linear_box_weight`` is no
+  longer zero.  Every (query, head, level) has its own box: centre = the query's pixel centre moved by
+  U(-1/2, 1/2) of the box size, width and height log-uniform in [2, 64] pixels of the finest level
+  (the init state is 4 px of the query's own level), then the same K x K grid.  Between the two
+  extremes above: neighbouring queries still look at neighbouring pixels, but footprints differ per
+  row and many exceed what a 64-pixel window holds.
 
 ``oob`` moves that fraction of the points outside [0,1] to exercise zero padding.
 """
@@ -137,11 +143,79 @@ def coco_encoder(B=1, K=4, dist="box", oob=0.0, heads=8, head_dim=32, image=(800
         loc = _grid_from_boxes(ref, offsets, K, K)
     elif dist == "uniform":
         loc = torch.rand(B, S, heads, L, K * K, 2, device=dev, generator=gen)
+    elif dist == "trained":
+        loc = _trained_like_grid(encoder_ref_windows(shapes, B, dev), shapes[0], heads, L, K, gen)
     else:
         raise ValueError(dist)
     loc = _apply_oob(loc, oob, gen)
     attn = _softmax_weights(B, S, heads, L, K, gen, dev)
     return Workload(f"coco_encoder_K{K}_{dist}", value, sh, start, loc, (attn,), K)
+
+
+def _trained_like_grid(ref, shape0, heads, L, K, gen, lo=2.0, hi=64.0):
+    """ref (B,S,4) -> (B,S,H,L,K*K,2): per-(query, head, level) boxes, sizes log-uniform in [lo, hi] pixels of level 0."""
+    B, S = ref.shape[:2]
+    dev = ref.device
+    h0, w0 = shape0
+    px = torch.exp(math.log(lo) + (math.log(hi) - math.log(lo)) * torch.rand(B, S, heads, L, 2, device=dev, generator=gen))
+    size = px / torch.tensor([w0, h0], device=dev, dtype=torch.float32)
+    centre = ref[:, :, None, None, :2] + (torch.rand(B, S, heads, L, 2, device=dev, generator=gen) - 0.5) * size
+    return (centre.unsqueeze(-2) + _kernel_offsets(K, K, dev) * size.unsqueeze(-2)).contiguous()
+
+
+def window_mode_fraction(w: Workload, cap: int = 64):
+    """Fraction of (row, level) pairs whose touched pixel range fits a `cap`-pixel footprint window (the window
+    kernels' fast mode, boxattn_window.cuh) -- the rest take the per-point walk.  Restates the kernels' range rule:
+    points inside the window test, floor(x) .. floor(x)+1 clamped to the level."""
+    loc = w.loc.float()
+    fits = []
+    for l, (h, wd) in enumerate(w.shapes.tolist()):
+        x = loc[:, :, :, l, :, 0] * wd - 0.5
+        y = loc[:, :, :, l, :, 1] * h - 0.5
+        inside = (x > -1) & (y > -1) & (x < wd) & (y < h)
+        big = 1 << 30
+        x0 = torch.where(inside, torch.floor(x), torch.full_like(x, big)).amin(-1).clamp_min(0)
+        x1 = torch.where(inside, torch.floor(x) + 1, torch.full_like(x, -big)).amax(-1).clamp_max(wd - 1)
+        y0 = torch.where(inside, torch.floor(y), torch.full_like(y, big)).amin(-1).clamp_min(0)
+        y1 = torch.where(inside, torch.floor(y) + 1, torch.full_like(y, -big)).amax(-1).clamp_max(h - 1)
+        nx, ny = x1 - x0 + 1, y1 - y0 + 1
+        fits.append(((nx * ny <= cap) | (nx <= 0) | (ny <= 0)).float().mean())
+    return float(torch.stack(fits).mean())
+
+
+def box3d_encoder(B=1, K=2, heads=8, head_dim=32, levels=((234, 234), (117, 117)), seed=7, device="cuda", ref_size=4.0) -> Workload:
+    """The reference-exact BoxeR-3D encoder call (note N1 / config c5): two BEV levels 234x234 + 117x117
+    (base_boxer3d_detection.yaml:132-146), C=256 (D=32), Nq = S = 68 445, 2x2 grid with the /2 index divisor
+    (box_attention.py:291), ``Box3dAttention(with_rotation=False)`` (box3d_transformer.py:233).  Reference windows as
+    ``Box3dTransformer._create_ref_windows`` (:57-110): centre = (i + 0.5) / size, size = ref_size / size, one window per
+    head whose fifth entry is the head's reference angle in *normalised* units -- which the non-rotating attention hands
+    to cos / sin as it is (box_attention.py:318-327), so every head's grid is turned by a fixed 0.5 .. 1.0 rad."""
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    sh, start = _level_meta(list(levels), dev)
+    S = int(sh.prod(1).sum())
+    L = len(levels)
+    value = torch.randn(B, S, heads, head_dim, device=dev, generator=gen)
+    ang = torch.tensor([0, 2 * math.pi / 3, -2 * math.pi / 3, 0, 2 * math.pi / 3, -2 * math.pi / 3, 0, math.pi], device=dev)
+    ang = ((ang + 0.5 * 2 * math.pi) / (2 * math.pi))[:heads]
+    refs = []
+    for h, w in levels:
+        ys = (torch.arange(h, device=dev, dtype=torch.float32) + 0.5) / h
+        xs = (torch.arange(w, device=dev, dtype=torch.float32) + 0.5) / w
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        box = torch.stack([xx, yy, torch.full_like(xx, ref_size / w), torch.full_like(yy, ref_size / h)], -1)
+        refs.append(box.reshape(h * w, 4))
+    ref = torch.cat(refs, 0)[None, :, None, None, :].expand(B, S, heads, 1, 4)
+    offsets = torch.rand(heads, L, 4, device=dev, generator=gen).expand(B, S, heads, L, 4)
+    boxes = ref + offsets / 8 * ref[..., [2, 3, 2, 3]]
+    center, size = boxes.unsqueeze(-2).split(2, dim=-1)
+    g = _kernel_offsets(K, 2, dev) * torch.relu(size)
+    angles = ang.view(1, 1, heads, 1).expand(B, S, heads, L)
+    c, s_ = torch.cos(angles), torch.sin(angles)
+    rot = torch.stack([c, -s_, s_, c], -1).view(B, S, heads, L, 1, 2, 2)
+    loc = (center + (g.unsqueeze(-2) * rot).sum(-1)).contiguous()
+    attn = _softmax_weights(B, S, heads, L, K, gen, dev)
+    return Workload(f"box3d_encoder_K{K}", value, sh, start, loc, (attn,), K)
 
 
 def random_boxes(B, Nq, gen, device):

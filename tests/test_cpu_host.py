@@ -178,6 +178,23 @@ def test_workload_generators_cpu():
     assert r.loc.shape == (1, 5, 8, 1, 9, 2)
 
 
+def test_trained_like_and_box3d_generators_cpu():
+    from boxer_b200 import workloads as W
+    t = W.coco_encoder(K=4, dist="trained", device="cpu", image=(64, 96))
+    assert t.loc.shape == (1, t.dims["S"], 8, 4, 16, 2)
+    # box extents are 2..64 px of level 0 (12 px wide here): per-(row, level) spread of x in level-0 pixels
+    x = t.loc[..., 0] * 12
+    ext = (x.amax(-1) - x.amin(-1)) * 4 / 3          # K=4 grid spans 3/4 of the box
+    assert 1.9 <= float(ext.min()) and float(ext.max()) <= 64.1
+    fb, ft, fu = (W.window_mode_fraction(W.coco_encoder(K=4, dist=d, device="cpu", image=(128, 192))) for d in ("box", "trained", "uniform"))
+    assert fb > ft > fu
+    e = W.box3d_encoder(device="cpu", levels=((12, 12), (6, 6)))
+    assert e.dims == dict(B=1, S=180, H=8, D=32, L=2, Nq=180, P=4)
+    # head 0: reference angle 0 -> normalised 0.5, used as radians (box_attention.py:318-327): the 2x2 grid is turned by 0.5 rad
+    d = e.loc[0, 0, 0, 0]
+    assert float(torch.atan2((d[1] - d[0])[1], (d[1] - d[0])[0])) == pytest.approx(0.5, abs=1e-4)
+
+
 def test_compat_install_maps_reference_import_paths():
     import boxer_b200
     boxer_b200.compat.install()
