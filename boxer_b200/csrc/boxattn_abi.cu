@@ -13,6 +13,7 @@
 #include "boxattn_instance.cuh"
 #include "boxattn_fused.cuh"
 #include "boxattn_staged.cuh"
+#include "boxattn_tile.cuh"
 #include "../../include/boxattn_b200.h"
 
 // Build-time slicing: the same source can be compiled once per (dtype, direction) slice, in parallel,
@@ -80,6 +81,9 @@ int sm_count() {
     return cache[dev];
 }
 
+#ifndef BXR_TILE_DEFAULT
+#define BXR_TILE_DEFAULT 0
+#endif
 #ifndef BXR_TRIM_CARVEOUT
 #define BXR_TRIM_CARVEOUT 1
 #endif
@@ -321,6 +325,67 @@ int dispatch_fwd_stg(int g, AttnParams& p, cudaStream_t st) {
     BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_stg<TV, G, SUB, PPL, MODE>(p, st)))
 }
 
+// ---- query-tile x value-tile kernels (boxattn_tile.cuh): self-attention-shaped calls (Nq == S: the queries are the
+// pixels), head_dim 32, at most 16 points per level, enough rows to fill the GPU
+template <typename TV>
+bool use_tile(const AttnParams& p, unsigned flags) {
+    if (std::is_same<TV, double>::value) return false;
+    if (flags & (BXR_FLAG_PATH_POINT | BXR_FLAG_PATH_WINDOW | BXR_FLAG_STAGED)) return false;
+    if (p.Nq != p.S || p.D != 32 || p.P < 1 || p.P > 16) return false;
+    if ((long long)p.B * p.S * p.H >= 0x7fffffffLL) return false;      // the kernels count (image, tile, head) items in 32 bits
+    if (flags & BXR_FLAG_PATH_TILE) return true;
+#if BXR_TILE_DEFAULT
+    return p.rows >= 16LL * sm_count() * kTileRows;
+#else
+    return false;
+#endif
+}
+
+template <void (*K)(const AttnParams)>
+int launch_tile(const AttnParams& p, size_t smem, cudaStream_t st, const char* name) {
+    static int occ[64] = {0};      // per device; immutable once set
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (occ[dev] == 0) {
+        BXR_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 0;
+        BXR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, kTileThreads, smem));
+        if (n <= 0) return fail(BXR_ERR_UNSUPPORTED, "tile kernel does not fit an SM");
+        // what is not shared memory is L1, which the unstaged gathers live on: ask for no more than the resident CTAs use
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, K) == cudaSuccess) {
+            const size_t need = (size_t)n * (smem + fa.sharedSizeBytes + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+        }
+        occ[dev] = n;
+    }
+    const int grid = sm_count() * occ[dev];
+    K<<<grid, kTileThreads, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    ++g_launches;
+    return BXR_OK;
+}
+
+template <typename TV, typename ACC>
+int bwd_tile(AttnParams& p, cudaStream_t st) {
+    const size_t smem = tile_smem_bytes(TileLane<TV>::ROWB, true);
+    const int ppl = (p.P + kTG - 1) / kTG;
+    if (ppl <= 1) return launch_tile<box_bwd_tile_kernel<TV, 1, ACC>>(p, smem, st, "box_bwd_tile_kernel");
+    if (ppl <= 2) return launch_tile<box_bwd_tile_kernel<TV, 2, ACC>>(p, smem, st, "box_bwd_tile_kernel");
+    return launch_tile<box_bwd_tile_kernel<TV, 4, ACC>>(p, smem, st, "box_bwd_tile_kernel");
+}
+
+template <typename TV>
+int fwd_tile(AttnParams& p, cudaStream_t st) {
+    const size_t smem = tile_smem_bytes(TileLane<TV>::ROWB, false);
+    const int ppl = (p.P + kTG - 1) / kTG;
+    if (ppl <= 1) return launch_tile<box_fwd_tile_kernel<TV, 1>>(p, smem, st, "box_fwd_tile_kernel");
+    if (ppl <= 2) return launch_tile<box_fwd_tile_kernel<TV, 2>>(p, smem, st, "box_fwd_tile_kernel");
+    return launch_tile<box_fwd_tile_kernel<TV, 4>>(p, smem, st, "box_fwd_tile_kernel");
+}
+
 // the fused (box -> grid) window kernels apply whenever the vector layout does; no row-count threshold
 bool fused_applies(int dtype_bytes, int B, int S, int H, int D, int L, int P, unsigned flags) {
     if (flags & BXR_FLAG_PATH_POINT) return false;
@@ -409,6 +474,9 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
     const int g = vec_group<TV>(D, p.LP);
     if (g && aligned16(value) && aligned16(out) && (!INSTANCE || aligned16(mask_out)) && aligned8(loc)) {
         if constexpr (!std::is_same<TV, double>::value) {
+            if constexpr (!INSTANCE) {
+                if (use_tile<TV>(p, flags)) return fwd_tile<TV>(p, st);
+            }
             if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
                 // (measured, r01j: the instance kernels are faster with 16-byte lanes, so only the box op switches)
                 if constexpr (!INSTANCE) {
@@ -557,6 +625,15 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
                                   (!fused->valid_ratios || aligned8(fused->valid_ratios)))
                                : (aligned8(loc) && aligned8(grad_loc)));
     if (fused && !vec_ok) return fail(BXR_ERR_UNSUPPORTED, "fused backward reached with a layout the fused kernels do not cover");
+    if constexpr (!std::is_same<TV, double>::value && !INSTANCE) {
+        if (vec_ok && !fused && use_tile<TV>(p, flags)) {
+            status = det ? bwd_tile<TV, long long>(p, st) : bwd_tile<TV, float>(p, st);
+            if (status) return status;
+            if (det) return finalize<TV, long long>(static_cast<const long long*>(acc), grad_value, n_value, scale, st);
+            if (sizeof(TV) == 2) return finalize<TV, float>(static_cast<const float*>(acc), grad_value, n_value, nullptr, st);
+            return BXR_OK;
+        }
+    }
     if constexpr (!std::is_same<TV, double>::value) {
         bool win = false;
         if constexpr (!INSTANCE) win = vec_ok && (fused ? true : use_window(p, g, flags));

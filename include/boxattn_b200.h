@@ -74,6 +74,9 @@ typedef enum bxr_status {
 #define BXR_FLAG_STAGED 0x8u        /* tuning/testing: footprint-window forward with TMA-staged row operands (cp.async.bulk
                                        + mbarrier per warp) and a pooled multi-level window; see boxattn_staged.cuh */
 
+#define BXR_FLAG_PATH_TILE 0x10u     /* tuning/testing: query-tile x value-tile kernels (TMA-staged value halos in shared
+                                       memory, boxattn_tile.cuh) whenever they apply (Nq == S, head_dim 32, P <= 16) */
+
 typedef void* bxr_stream_t;   /* a cudaStream_t */
 typedef uint16_t bxr_bf16;    /* raw bfloat16 bits */
 

@@ -17,9 +17,11 @@ ap.add_argument("--dist", default="box")
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("--det", action="store_true")
+ap.add_argument("--path", default="auto")
 a = ap.parse_args()
 dt = {"f32": torch.float32, "bf16": torch.bfloat16}[a.dtype]
 ops.set_deterministic(a.det)
+ops.set_kernel_path(a.path)
 if a.workload == "enc":
     w = W.coco_encoder(K=a.K, dist=a.dist, device="cuda")
 elif a.workload == "dec":

@@ -85,6 +85,20 @@ def test_c2_encoder_full_size_elementwise(K, dist, dtype):
     _box_case(W.coco_encoder(K=K, dist=dist, oob=0.02 if dist != "box" else 0.0, device=DEV), dtype)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("dist,K", [("box", 4), ("trained", 4), ("box", 2)])
+def test_c2_encoder_full_size_tile_kernels(dist, K, dtype):
+    """The same full-size comparison through the query-tile x value-tile kernels (boxattn_tile.cuh): staged windows
+    (box), windows that left their tile's halo and wide footprints (trained-like)."""
+    from boxer_b200 import workloads as W
+    b = _ops()
+    b.ops.set_kernel_path("tile")
+    try:
+        _box_case(W.coco_encoder(K=K, dist=dist, oob=0.02 if dist != "box" else 0.0, device=DEV), dtype)
+    finally:
+        b.ops.set_kernel_path("auto")
+
+
 def test_c2_encoder_full_size_batch2_deterministic():
     """B = 2 images per GPU (BASELINE configs[2]'s per-GPU batch) through the deterministic scatter, element-wise."""
     from boxer_b200 import workloads as W
@@ -95,6 +109,16 @@ def test_c2_encoder_full_size_batch2_deterministic():
     _check(out, ref_out, 1e-4, "out")
     _check(grads[0], ref[0], 1e-4, "grad_value (deterministic)")
     _check(grads[2], ref[2], 1e-4, "grad_attn")
+    b = _ops()
+    b.ops.set_kernel_path("tile")       # and the tile kernels' deterministic scatter, B = 2
+    try:
+        out_t, grads_t = _run_box(_wl_inputs(w), torch.float32, go, deterministic=True)
+        grads_t2 = _run_box(_wl_inputs(w), torch.float32, go, deterministic=True)[1]
+    finally:
+        b.ops.set_kernel_path("auto")
+    _check(out_t, ref_out, 1e-4, "out (tile)")
+    _check(grads_t[0], ref[0], 1e-4, "grad_value (tile, deterministic)")
+    assert torch.equal(grads_t[0], grads_t2[0]), "deterministic scatter must be bit-reproducible"
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])

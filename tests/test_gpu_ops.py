@@ -295,11 +295,13 @@ def test_instance_mask_head_vs_oracle(K, Nq, dtype):
 
 # ============================================================== footprint-window kernels, forced at small sizes
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
-@pytest.mark.parametrize("path", ["window", "window-staged"])
+@pytest.mark.parametrize("path", ["window", "window-staged", "tile"])
 @pytest.mark.parametrize("case", ["enc_box_K4", "enc_box_K2", "enc_uniform_K4", "enc_box_K3_oob", "dec_K4", "bev_K3", "enc_box_K5"])
 def test_window_kernels_vs_oracle(case, dtype, path):
     """Same op through the footprint-window kernels (forced with set_kernel_path) on small inputs:
-    window mode (box-structured), per-point fallback (uniform / wide boxes), borders and padding."""
+    window mode (box-structured), per-point fallback (uniform / wide boxes), borders and padding.
+    "tile": the query-tile x value-tile kernels (TMA-staged value halos; they apply to the encoder-shaped cases with
+    head_dim 32 and fall through to the default kernels elsewhere)."""
     from boxer_b200 import workloads as W
     b = _ops()
     img = (72, 100)
