@@ -144,12 +144,19 @@ def step_resident(ops, w, go):
     return out, grads, n + ops.last_launch_count()
 
 
-def max_over_ranks(ms: float, device) -> float:
+PER_RANK_MS = {}       # label -> this run's per-rank device times (filled under torchrun; reported in the JSON line)
+
+
+def max_over_ranks(ms: float, device, label: str = "") -> float:
     """A multi-GPU number is the slowest rank's device time (never wall clock, never the mean)."""
     import torch.distributed as dist
     t = torch.tensor([ms], device=device, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    allt = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(allt, t)
+    vals = [float(x.item()) for x in allt]
+    if label:
+        PER_RANK_MS[label] = vals
+    return max(vals)
 
 
 def rank_seed(rank: int, base: int = 3) -> int:
@@ -177,7 +184,9 @@ def timed(fn, steps, warmup, dist_on):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if dist_on:
-        ms = max_over_ranks(ms, "cuda")
+        ms = max_over_ranks(ms, "cuda", "resident")
+    else:
+        PER_RANK_MS["resident"] = [ms]
     return ms
 
 
@@ -290,7 +299,9 @@ def e2e_run(sets, steps, warmup, dist_on):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if dist_on:
-        ms = max_over_ranks(ms, "cuda")
+        ms = max_over_ranks(ms, "cuda", "e2e")
+    else:
+        PER_RANK_MS["e2e"] = [ms]
     return ms, h2d, d2h
 
 
@@ -335,8 +346,9 @@ def run_reference(args, rank):
     if rank != 0:
         return
     w, go = cpu_workload(CFG["K"])
-    total = args.steps + args.warmup
-    frac = min(1.0, 24.0 / max(1, total))      # keep the whole run within a few minutes of CPU time
+    cores = torch.get_num_threads()
+    frac = 1.0      # every step is one pass over the FULL config (all queries): ~0.8 s on the box's host cores,
+                    # so the driver's 20 + 5 steps take ~20 s and `config` equals the repo arm's
     for _ in range(args.warmup):
         cpu_pass(w, go, frac)
     t, n = 0.0, 0
@@ -345,17 +357,142 @@ def run_reference(args, rank):
         t += dt
         n += ns
     val = n / t / 1e9
-    cores = torch.get_num_threads()
-    sample = (f"each step = fwd+bwd of the grid_sample formulation over the first {frac:.3f} of the {CFG['Nq']} queries "
-              f"(all 4 levels, K=4, fp32), {args.steps} steps, {cpu_model()}")
+    sample = (f"each step = fwd+bwd of the reference's grid_sample formulation (oracle/plain.py) over all {CFG['Nq']} queries "
+              f"(4 levels, K=4, fp32) = the full config, {args.steps} steps, {cores} threads, {cpu_model()}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(CFG, query_fraction=frac),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(CFG),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def compulsory(n_samples, d, ms, peak, backward, dram_bytes):
+    """Bytes that must cross HBM once for one launch (fp32): value + loc + weights (+ grad_out) in, out (or the three
+    gradients, with grad_value zero-filled first) out."""
+    rows = d["B"] * d["Nq"] * d["H"]
+    value = d["B"] * d["S"] * d["H"] * d["D"] * 4
+    loc, wts, out = n_samples * 8, n_samples * 4, rows * d["D"] * 4
+    b = value + loc + wts + (out + 2 * value + loc + wts if backward else out)
+    r = {"bytes": b, "GBs": b / (ms * 1e-3) / 1e9, "frac": b / (ms * 1e-3) / 1e9 / peak, "ms_per_launch": ms}
+    if dram_bytes:
+        r["measured_dram_bytes"] = dram_bytes
+        r["frac_measured_dram"] = dram_bytes / (ms * 1e-3) / 1e9 / peak
+    return r
+
+
+def reference_cuda_subprocess():
+    """fwd / bwd time of the UNMODIFIED reference CUDA kernels (oracle/_ref, compiled for sm_100a from /root/reference by
+    oracle/build_ref.py) at the headline config, measured in a SEPARATE process so that this process never loads
+    anything but libboxattn_b200.so.  None when the comparison build is absent."""
+    script = os.path.join(ROOT, "scripts", "compare_reference_cuda.py")
+    out = os.path.join(ROOT, "gpurun_out", "reference_cuda_headline.json")
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        proc = subprocess.run([sys.executable, script, out, "--headline-only"], capture_output=True, text=True, timeout=240)
+        if proc.returncode != 0:
+            return {"unavailable": (proc.stderr or proc.stdout).strip().splitlines()[-1][:200] if (proc.stderr or proc.stdout) else "failed"}
+        with open(out) as f:
+            r = json.load(f)["enc_K4_box"]
+        return {"fwd_ms": r["ref_fwd_ms"], "bwd_ms": r["ref_bwd_ms"], "fwdbwd_Gsamples_per_s": r["n_samples"] / (r["ref_fwd_ms"] + r["ref_bwd_ms"]) / 1e6,
+                "ours_same_process": {"fwd_ms": r["ours_fwd_ms"], "bwd_ms": r["ours_bwd_ms"]},
+                "speedup_fwd": r["speedup_fwd"], "speedup_bwd": r["speedup_bwd"], "speedup_fwdbwd": r["speedup_fwdbwd"],
+                "how": "subprocess scripts/compare_reference_cuda.py --headline-only: the reference's own box_attn_forward / "
+                       "box_attn_backward (vision.cpp:8-9) from oracle/_ref on the same GPU, same tensors, CUDA events, mean of 20 / 5 launches"}
+    except Exception as e:       # a comparison point, never a reason to lose the bench line
+        return {"unavailable": str(e)[:200]}
+
+
+def model_leg(dev):
+    """BASELINE configs[2] on one GPU's share: the reference's UNMODIFIED BoxTransformer (6 encoder + 6 decoder layers,
+    d_model 256, 8 heads, 4 levels, FFN 1024, 300 queries, use_mask -> InstanceAttention 14 x 14 in every decoder
+    layer; box_transformer.py:16-465, loaded from the bytecode baseline/build_ref_layers.py compiled) running on the
+    drop-in, forward + backward, B = 2 images per GPU padded to the batch maximum with masks (collate_fn.py:66-84),
+    synthetic 800 x 1333 feature pyramids.  Three precisions: fp32; bf16 autocast with the reference's AMP contract (the
+    op force-casts to fp32, box_attention_func.py:11); bf16 autocast with boxer_b200.set_amp_native (bf16 value / outputs).
+    Reports ms per iteration and the share of it spent inside the four native ops (CUDA events around every call)."""
+    import boxer_b200
+    from boxer_b200 import ops as ops_mod
+    from boxer_b200 import workloads as W
+    try:
+        from baseline import ref_layers as R
+        if not R.available():
+            return {"unavailable": "baseline/_ref not built (python -m baseline.build_ref_layers where /root/reference exists)"}
+        bt, _ = R.import_layers("boxer_b200")
+    except Exception as e:
+        return {"unavailable": str(e)[:200]}
+    model = R.make_boxer2d(bt, d_model=256, nhead=8, nlevel=4, enc=6, dec=6, ffn=1024, num_queries=300, use_mask=True).to(dev)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():        # trained-like: non-zero box / attention projections
+        for n, p_ in model.named_parameters():
+            if "linear_box_weight" in n or "linear_attn_weight" in n:
+                p_.copy_((0.02 * torch.randn(p_.shape, generator=g)).to(dev))
+    src, mask, pos = R.padded_batch(W.fpn_levels(), 2, 256, valid=[(1.0, 1.0), (0.8, 0.75)], device=dev)
+    names = ("box_attn_forward", "box_attn_backward", "instance_attn_forward", "instance_attn_backward")
+    orig = {n: getattr(ops_mod, n) for n in names}
+    events = []
+
+    def wrap(n):
+        def f(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig[n](*a, **k)
+            e1.record()
+            events.append((n, e0, e1))
+            return r
+        return f
+
+    def step(amp, native):
+        boxer_b200.set_amp_native(native)
+        for p_ in model.parameters():
+            p_.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            hs, roi = model(src, mask, pos)[:2]
+            loss = hs.float().square().mean() + roi.float().square().mean()
+        loss.backward()
+
+    out = {"config": "6+6 layers, d_model 256, 8 heads, FFN 1024, 300 queries, use_mask, B=2 (second image 0.8 x 0.75 of the padded size), "
+                     "S=22223, encoder K=2, decoder InstanceAttention K=14; reference layers unmodified on boxer_b200"}
+    try:
+        for label, amp, native in (("fp32", False, False), ("bf16_autocast_reference_amp", True, False), ("bf16_autocast_native", True, True)):
+            for _ in range(2):
+                step(amp, native)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a.record()
+            for _ in range(reps):
+                step(amp, native)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+            for n in names:
+                setattr(ops_mod, n, wrap(n))
+            events.clear()
+            step(amp, native)
+            torch.cuda.synchronize()
+            for n in names:
+                setattr(ops_mod, n, orig[n])
+            per = {}
+            for n, e0, e1 in events:
+                per.setdefault(n, [0, 0.0])
+                per[n][0] += 1
+                per[n][1] += e0.elapsed_time(e1)
+            op_ms = sum(v[1] for v in per.values())
+            out[label] = {"ms_per_iteration": ms, "native_op_ms": op_ms, "native_op_share": op_ms / ms,
+                          "ops": {n: {"calls": v[0], "ms": v[1]} for n, v in per.items()},
+                          "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    except Exception as e:
+        out["error"] = str(e)[:300]
+    finally:
+        for n in names:
+            setattr(ops_mod, n, orig[n])
+        boxer_b200.set_amp_native(False)
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------ main
@@ -465,6 +602,37 @@ def variants(ops, dev, bw_peak):
             o["fused_softmax_bwd_ms"] = time_call(lambda: ops.box_grid_attn_backward(v4, w.shapes, w.level_start, boxes, None, None, kidx, attn, go_m, 64, softmax=True))
             o["torch_softmax_fwd_ms"] = time_call(lambda: torch.softmax(logits.view(1, S, 8, -1), -1))
         res[f"op_box_grid_K{K}"] = o
+
+    res["model_configs2_BoxTransformer"] = model_leg(dev)
+
+    # InstanceAttention module (mask head input path, rows f3 / f4): fwd+bwd, fp32 vs autocast with the reference's AMP
+    # contract (op in fp32, two fp32 -> bf16 conversions in front of out_proj) vs set_amp_native (bf16 written once)
+    for K in (14, 28):
+        torch.manual_seed(0)
+        im = boxer_b200.InstanceAttention(256, 4, 8, K).to(dev)
+        im.inferencing = False
+        with torch.no_grad():
+            im.linear_box_weight.normal_(0, 0.02)
+            im.linear_attn_weight.normal_(0, 0.05)
+        qi = torch.randn(1, 300, 256, device=dev, requires_grad=True)
+        mem = torch.randn(1, S, 256, device=dev, requires_grad=True)
+        gen = torch.Generator(device=dev).manual_seed(5)
+        refb = W.random_boxes(1, 300, gen, dev)
+        r = {}
+        for label, amp, native in (("fp32_ms", False, False), ("autocast_reference_amp_ms", True, False), ("autocast_native_ms", True, True)):
+            boxer_b200.set_amp_native(native)
+
+            def run_inst():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    o, mo, _ = im(qi, mem, w.shapes, None, w.level_start, None, refb)
+                    loss = o.float().sum() + mo.float().sum()
+                loss.backward()
+
+            r[label] = time_call(run_inst, reps=10)
+        boxer_b200.set_amp_native(False)
+        r["native_vs_reference_amp"] = r["autocast_reference_amp_ms"] / r["autocast_native_ms"]
+        res[f"module_InstanceAttention_K{K}_fwdbwd"] = r
+        del im, qi, mem
 
     # warm vs L2-flushed: one launch at a time, a 512 MB write in between evicts value / loc from L2
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -582,6 +750,13 @@ def main():
     uf_ms, ub_ms = kernel_times(ops, uni, 10)
     uf_ms, ub_ms = kernel_times(ops, uni, 20)
     del uni
+    # third distribution: trained-like encoder boxes (per-query offsets, sizes log-uniform in 2..64 px) -- between the
+    # init-state headline (every window fits the 64-pixel footprint) and uniform points (none does)
+    trn = make_sets(dev, 1, seed0=rank_seed(rank) + 200, K=CFG["K"], dist="trained", B=CFG["B_per_gpu"])
+    tf_ms, tb_ms = kernel_times(ops, trn, 10)
+    tf_ms, tb_ms = kernel_times(ops, trn, 20)
+    win_frac = {"box": W.window_mode_fraction(sets[0][0]), "trained": W.window_mode_fraction(trn[0][0])}
+    del trn
 
     def dram(tr, ms):      # measured DRAM bytes of the committed ncu capture over the live launch time
         return None if tr is None else {"GBs": tr / (ms * 1e-3) / 1e9, "frac_of_peak": tr / (ms * 1e-3) / 1e9 / bw_peak}
@@ -606,7 +781,22 @@ def main():
                          "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6, "dram": dram(tr_f, kf_ms), "issue_active_pct_ncu": is_f},
         "uniform_locations": {"fwd_ms": uf_ms, "bwd_ms": ub_ms, "fwdbwd_Gsamples_per_s": n_samples / (uf_ms + ub_ms) / 1e6,
                               "note": "same sizes, sampling points drawn uniformly in [0,1)^2 (no spatial structure)"},
+        "trained_like_locations": {"fwd_ms": tf_ms, "bwd_ms": tb_ms, "fwdbwd_Gsamples_per_s": n_samples / (tf_ms + tb_ms) / 1e6,
+                                   "window_mode_fraction": win_frac["trained"], "window_mode_fraction_headline": win_frac["box"],
+                                   "note": "same sizes; every (query, head, level) has its own box: centre = pixel centre +- U(1/2) box, "
+                                           "width / height log-uniform in 2..64 px of level 0; window_mode_fraction = share of (row, level) "
+                                           "pairs whose footprint fits the 64-pixel window (the rest take the per-point walk)"},
         "roofline_step": {"achieved": ach_s, "frac": ach_s / bw_peak, "unit": "GB/s"},
+        # what the kernels can physically be held against: the bytes that MUST cross HBM (compulsory: every input read
+        # once, every output written once; grad_value also zero-filled) and the bytes that did (ncu, dram__bytes_*),
+        # each over the live kernel time and the measured HBM peak
+        "roofline_compulsory": {
+            "bound": "hbm", "peak": bw_peak, "unit": "GB/s",
+            "fwd": compulsory(n_samples, d, kf_ms, bw_peak, False, tr_f),
+            "bwd": compulsory(n_samples, d, kb_ms, bw_peak, True, tr_b),
+            "note": "frac = compulsory bytes / kernel time / peak; frac_measured_dram = ncu DRAM bytes of the committed capture / "
+                    "live kernel time / peak.  These, not the no-reuse model above, say how far the kernels are from the HBM bound: "
+                    "value (22.8 MB) is L2-resident, so the kernels are bound by instruction issue and gather latency"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                 "host_cpus": ("NUMA-local to the GPU: %d cpus" % len(local)) if local else "unpinned",
@@ -616,6 +806,13 @@ def main():
         "clocks": clocks,
     }
 
+    line["per_rank_ms_per_step"] = {
+        k: {"min": min(v) / n, "median": statistics.median(v) / n, "max": max(v) / n, "ranks": len(v)}
+        for k, v, n in (("resident", PER_RANK_MS.get("resident", []), args.steps), ("e2e", PER_RANK_MS.get("e2e", []), e2e_steps)) if v}
+    line["per_rank_note"] = ("every rank times its own images (seed 3 + 10 * rank); `value` uses the slowest rank.  Under torchrun the "
+                             "timed region starts right after an NCCL barrier (idle gap + collective tail), which N = 1 does not have")
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        line["reference_cuda"] = reference_cuda_subprocess()
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         cw, cgo = cpu_workload(CFG["K"])
         cpu_pass(cw, cgo, 0.25)                      # warm-up on a quarter of the queries

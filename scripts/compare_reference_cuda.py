@@ -28,12 +28,18 @@ def time_call(fn, reps=20):
     return a.elapsed_time(b) / reps
 
 
-def main(out_path):
+def main(out_path, headline_only=False):
     ref = ref_cuda.load()
     res = {}
-    for name, w in (("enc_K4_box", W.coco_encoder(K=4, device="cuda")), ("enc_K2_box", W.coco_encoder(K=2, device="cuda")),
-                    ("enc_K4_uniform", W.coco_encoder(K=4, dist="uniform", device="cuda")),
-                    ("dec_K2", W.coco_decoder(K=2, device="cuda")), ("bev_B8_K3", W.bev_rotated(B=8, device="cuda"))):
+    cases = [("enc_K4_box", lambda: W.coco_encoder(K=4, device="cuda"))]
+    if not headline_only:
+        cases += [("enc_K2_box", lambda: W.coco_encoder(K=2, device="cuda")),
+                  ("enc_K4_uniform", lambda: W.coco_encoder(K=4, dist="uniform", device="cuda")),
+                  ("enc_K4_trained", lambda: W.coco_encoder(K=4, dist="trained", device="cuda")),
+                  ("dec_K2", lambda: W.coco_decoder(K=2, device="cuda")), ("bev_B8_K3", lambda: W.bev_rotated(B=8, device="cuda")),
+                  ("box3d_enc_K2", lambda: W.box3d_encoder(device="cuda"))]
+    for name, mk in cases:
+        w = mk()
         B, Nq = w.loc.shape[:2]
         go = torch.randn(B, Nq, w.value.shape[2] * w.value.shape[3], device="cuda")
         a = (w.value, w.shapes, w.level_start, w.loc, w.weights[0])
@@ -46,7 +52,7 @@ def main(out_path):
         r["speedup_bwd"] = r["ref_bwd_ms"] / r["ours_bwd_ms"]
         r["speedup_fwdbwd"] = (r["ref_fwd_ms"] + r["ref_bwd_ms"]) / (r["ours_fwd_ms"] + r["ours_bwd_ms"])
         res[name] = r
-    for K in (14,):
+    for K in (() if headline_only else (14, 28)):
         m = W.coco_mask_head(K=K, device="cuda")
         go = torch.randn(1, 300, 256, device="cuda")
         gm = torch.randn(1, 300, K * K, 256, device="cuda")
@@ -67,4 +73,5 @@ def main(out_path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "vs_reference_cuda.json"))
+    main(sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else os.path.join(ROOT, "gpurun_out", "vs_reference_cuda.json"),
+         headline_only="--headline-only" in sys.argv)
