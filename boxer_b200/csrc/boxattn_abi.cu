@@ -235,14 +235,50 @@ bool use_window(const AttnParams& p, int g, unsigned flags) {
     return p.rows >= 2LL * sm_count() * groups;     // small (decoder-sized) calls keep the point-split kernels
 }
 
+// Tile-ordered work units (boxattn_window.cuh, TileOrder) for self-attention-shaped calls: Nq == S, rows of 8 lanes
+// (head_dim 32 fp32 / bf16 with 8-byte lanes), location-taking op.  The unit count then depends on the level shapes,
+// which live on the device: the kernel derives it, the host only sizes the persistent grid.
+// MEASURED AND NOT ADOPTED (B200, r02k, profiles/README.md): the L1 sector hit rate of the forward goes from 29 % to 72 %
+// as intended, and nothing else moves -- long-scoreboard stalls 3.08 -> 2.72 cycles per issue, 137 M instead of 133 M
+// instructions, forward 0.178 -> 0.191 ms, backward 0.350 -> 0.353 ms, uniform / trained-like 10-17 % slower (the rows of
+// a unit are 4 KB apart in loc / weights instead of contiguous).  Where the gathered rows come from is not what these
+// kernels wait for.  BXR_WIN_TILED=1 compiles the variant (selected unless BXR_FLAG_NO_TILE_ORDER is given).
+#ifndef BXR_WIN_TILED
+#define BXR_WIN_TILED 0
+#endif
+bool use_tiled_units(const AttnParams& p, int G, unsigned flags) {
+#if BXR_WIN_TILED
+    if (flags & BXR_FLAG_NO_TILE_ORDER) return false;
+    if (G != 8 || p.Nq != p.S || (long long)p.B * p.S * p.H >= 0x7fffffffLL) return false;
+    return (flags & BXR_FLAG_PATH_WINDOW) || p.rows >= 2LL * sm_count() * (kThreads / G);
+#else
+    (void)p; (void)G; (void)flags;
+    return false;
+#endif
+}
+
 template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX>
-int fwd_win(AttnParams& p, cudaStream_t st) {
+int fwd_win(AttnParams& p, cudaStream_t st, unsigned flags = 0) {
     p.units = (int)((p.rows + kFwdThreads / G - 1) / (kFwdThreads / G));
+#if BXR_WIN_TILED
+    if constexpr (G == 8 && !FUSED && !SMAX) {
+        if (use_tiled_units(p, G, flags))
+            return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED, SMAX, true>, kFwdThreads>(p, st, "box_fwd_win_kernel");
+    }
+#endif
+    (void)flags;
     return launch_units<box_fwd_win_kernel<TV, G, SUB, PPL, FUSED, SMAX>, kFwdThreads>(p, st, "box_fwd_win_kernel");
 }
 template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX>
-int bwd_win(AttnParams& p, cudaStream_t st) {
+int bwd_win(AttnParams& p, cudaStream_t st, unsigned flags = 0) {
     p.units = (int)((p.rows + kBwdThreads / G - 1) / (kBwdThreads / G));
+#if BXR_WIN_TILED
+    if constexpr (G == 8 && !FUSED && !SMAX) {
+        if (use_tiled_units(p, G, flags))
+            return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED, SMAX, true>, kBwdThreads>(p, st, "box_bwd_win_kernel");
+    }
+#endif
+    (void)flags;
     return launch_units<box_bwd_win_kernel<TV, G, SUB, PPL, ACC, FUSED, SMAX>, kBwdThreads>(p, st, "box_bwd_win_kernel");
 }
 
@@ -269,12 +305,12 @@ int win_key(int P, int g) {
 }
 
 template <typename TV, bool FUSED = false, bool SMAX = false>
-int dispatch_fwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_win<TV, G, SUB, PPL, FUSED, SMAX>(p, st)))
+int dispatch_fwd_win(int g, AttnParams& p, cudaStream_t st, unsigned flags = 0) {
+    BXR_DISPATCH_WIN(win_key(p.P, g), (fwd_win<TV, G, SUB, PPL, FUSED, SMAX>(p, st, flags)))
 }
 template <typename TV, typename ACC, bool FUSED = false, bool SMAX = false>
-int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st) {
-    BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC, FUSED, SMAX>(p, st)))
+int dispatch_bwd_win(int g, AttnParams& p, cudaStream_t st, unsigned flags = 0) {
+    BXR_DISPATCH_WIN(win_key(p.P, g), (bwd_win<TV, G, SUB, PPL, ACC, FUSED, SMAX>(p, st, flags)))
 }
 
 // ---- staged-row kernels (boxattn_staged.cuh): the window algorithm with TMA-staged row operands.
@@ -483,13 +519,13 @@ int forward(const TV* value, const int64_t* shapes, const int64_t* level_start, 
                     if (const int g8 = bf16_lane8_group(D)) {
                         if (use_window(p, g8, flags))
                             return use_staged(p, g8, 0, 1, flags) ? dispatch_fwd_stg<bf16x4_t, 0>(g8, p, st)
-                                                                  : dispatch_fwd_win<bf16x4_t>(g8, p, st);
+                                                                  : dispatch_fwd_win<bf16x4_t>(g8, p, st, flags);
                     }
                 }
             }
             if constexpr (!INSTANCE) {
                 if (use_window(p, g, flags))
-                    return use_staged(p, g, 0, 1, flags) ? dispatch_fwd_stg<TV, 0>(g, p, st) : dispatch_fwd_win<TV>(g, p, st);
+                    return use_staged(p, g, 0, 1, flags) ? dispatch_fwd_stg<TV, 0>(g, p, st) : dispatch_fwd_win<TV>(g, p, st, flags);
             } else {
 #if BXR_INST_FWD_BF16X4
                 if constexpr (std::is_same<TV, __nv_bfloat16>::value) {
@@ -650,13 +686,13 @@ int backward(const TV* value, const int64_t* shapes, const int64_t* level_start,
             if constexpr (!INSTANCE) {
                 if (fused && fused->softmax) status = det ? dispatch_bwd_win<bf16x4_t, long long, true, true>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float, true, true>(g8, p, st);
                 else if (fused) status = det ? dispatch_bwd_win<bf16x4_t, long long, true>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float, true>(g8, p, st);
-                else status = det ? dispatch_bwd_win<bf16x4_t, long long>(g8, p, st) : dispatch_bwd_win<bf16x4_t, float>(g8, p, st);
+                else status = det ? dispatch_bwd_win<bf16x4_t, long long>(g8, p, st, flags) : dispatch_bwd_win<bf16x4_t, float>(g8, p, st, flags);
             }
         } else if (win) {
             if constexpr (!INSTANCE) {
                 if (fused && fused->softmax) status = det ? dispatch_bwd_win<TV, long long, true, true>(g, p, st) : dispatch_bwd_win<TV, float, true, true>(g, p, st);
                 else if (fused) status = det ? dispatch_bwd_win<TV, long long, true>(g, p, st) : dispatch_bwd_win<TV, float, true>(g, p, st);
-                else status = det ? dispatch_bwd_win<TV, long long>(g, p, st) : dispatch_bwd_win<TV, float>(g, p, st);
+                else status = det ? dispatch_bwd_win<TV, long long>(g, p, st, flags) : dispatch_bwd_win<TV, float>(g, p, st, flags);
             }
         } else if (own) {
             if constexpr (INSTANCE) {

@@ -301,6 +301,56 @@ __device__ __forceinline__ void zero_window(T* win, int n4, int slane) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile-ordered work units (self-attention-shaped calls, Nq == S: the queries are the pixels of the value pyramid and
+// every query's box sits on its own pixel, box_transformer.py:70-116).  With rows dealt in memory order a work unit is
+// "2 (4) consecutive queries x all heads": the heads share nothing (each gathers its own 128-byte slice of a pixel) and
+// the queries of the units a CTA sees next are far away, so the ~80 % overlap between the footprints of neighbouring
+// queries never meets in one L1 (ncu r01x: sector hit rate 29 %).  Here a unit is a TW x TH tile of queries of one level
+// for ONE head -- a warp takes a tile line -- so that the rows a CTA works on at the same time gather the same pixels
+// (the tile's footprint: 131 pixels for a 4 x 4 tile against 720 window slots) and L1 serves them.  The order of the units
+// is a schedule, not an assumption: any row is still processed by the general algorithm.
+template <int TW, int TH>
+struct TileOrder {
+    int before[kMaxLevels + 1];      // tiles of the levels processed before level order k (coarse levels first)
+};
+
+template <int TW, int TH>
+__device__ __forceinline__ void tile_order_init(TileOrder<TW, TH>& t, const LevelTable& lv, int L) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < L; ++k) {
+            const int l = L - 1 - k;
+            t.before[k] = acc;
+            acc += ((lv.w[l] + TW - 1) / TW) * ((lv.h[l] + TH - 1) / TH);
+        }
+        t.before[L] = acc;
+    }
+    __syncthreads();
+}
+
+// unit -> this group's row (or -1): unit = ((image * tiles + tile) * H + head), group gid = (line, column) of the tile
+template <int TW, int TH>
+__device__ __forceinline__ long long tile_order_row(const TileOrder<TW, TH>& t, const LevelTable& lv, const AttnParams& p, unsigned u, int gid) {
+    const unsigned H = (unsigned)p.H;
+    const unsigned v = u / H;
+    const int head = (int)(u - v * H);
+    const unsigned tiles = (unsigned)t.before[p.L];
+    const unsigned b = v / tiles;
+    const int ti = (int)(v - b * tiles);
+    int k = 0;
+    while (k + 1 < p.L && t.before[k + 1] <= ti) ++k;
+    const int l = p.L - 1 - k;
+    const int tl = ti - t.before[k];
+    const int ntx = (lv.w[l] + TW - 1) / TW;
+    const int ty = tl / ntx, tx = tl - ty * ntx;
+    const int x = tx * TW + gid % TW, y = ty * TH + gid / TW;
+    if (x >= lv.w[l] || y >= lv.h[l]) return -1;
+    const long long q = lv.start[l] + (long long)y * lv.w[l] + x;
+    if (q >= p.Nq) return -1;
+    return ((long long)b * p.Nq + q) * p.H + head;
+}
+
 // what every lane of the group needs to know about one level of the current pass
 struct SubWin {
     int X0, Y0, nx, ny;   // touched pixel range (clamped to the level); nx <= 0: nothing inside
@@ -311,7 +361,7 @@ struct SubWin {
 // ------------------------------------------------------------------------------------------------
 // Forward.  One group of G lanes per row; work units (256/G rows) dealt round-robin to the CTAs.
 // SMAX (with FUSED): `w0` holds logits; the softmax over the row's L*P points is taken here and written to attn_out.
-template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX = false>
+template <typename TV, int G, int SUB, int PPL, bool FUSED, bool SMAX = false, bool TILED = false>
 __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PPL, FUSED, std::is_same<TV, float>::value, SUB < G)) box_fwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax prologue is built for the fused entry points only");
     using V = Vec16<TV>;
@@ -324,6 +374,14 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
     constexpr bool TAB = FwdSlotTable<TV>::value;
     __shared__ __align__(16) uint2 s_tab[TAB ? GROUPS * kTabPitch : 2];
     load_levels(lv, p);
+    // tile-ordered units: a warp (32 / G rows) is a tile line, the CTA a tile of (32 / G) x (warps) queries of one head
+    constexpr int TW = 32 / G, TH = kFwdThreads / 32;
+    __shared__ TileOrder<TW, TH> s_order;
+    int n_units = p.units;
+    if constexpr (TILED) {
+        tile_order_init(s_order, lv, p.L);
+        n_units = (int)((unsigned)p.B * (unsigned)s_order.before[p.L] * (unsigned)p.H);
+    }
 
     const int lane = threadIdx.x % G;
     const int gid = threadIdx.x / G;
@@ -341,12 +399,13 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
     // units are dealt round-robin: rows of the coarse levels (wide windows -> per-point fallback) cost
     // several times more than level-0 rows, and a contiguous split leaves the CTAs that own them as a tail
 #if BXR_UNIT_REVERSE
-    for (int u = p.units - 1 - (int)blockIdx.x; u >= 0; u -= gridDim.x) {
+    for (int u = (TILED ? (int)blockIdx.x : n_units - 1 - (int)blockIdx.x); TILED ? (u < n_units) : (u >= 0); u += TILED ? (int)gridDim.x : -(int)gridDim.x) {
 #else
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 #endif
-        const long long row_raw = (long long)u * GROUPS + gid;
-        const bool ract = row_raw < p.rows;     // groups past the last row stay with their warp, doing nothing
+        // (the tile order lists the coarse levels first by construction: no reversal needed there)
+        const long long row_raw = TILED ? tile_order_row(s_order, lv, p, (unsigned)u, gid) : (long long)u * GROUPS + gid;
+        const bool ract = TILED ? (row_raw >= 0) : (row_raw < p.rows);     // groups without a row stay with their warp, doing nothing
         const long long row = ract ? row_raw : 0;
         const int head = (int)(row % p.H);
         const long long b = row / ((long long)p.H * p.Nq);
@@ -600,7 +659,7 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
 
 // SMAX (with FUSED): `w0` holds the softmax weights the forward wrote; the weight gradients are chained through
 // the softmax before they leave the kernel:  grad_logit = w * (grad_w - sum_row(w * grad_w)).
-template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX = false>
+template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX = false, bool TILED = false>
 __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThreads / kBwdThreads) : kBwdMinB) box_bwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax epilogue is built for the fused entry points only");
     using V = Vec16<TV>;
@@ -615,6 +674,13 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     constexpr bool TABB = (BXR_BWD_TAB != 0) && G >= 8;     // G = 4: 64 groups per CTA, the table would not fit 48 KB
     __shared__ __align__(16) uint2 s_tab[TABB ? GROUPS * kTabPitch : 2];
     load_levels(lv, p);
+    constexpr int TW = 32 / G, TH = kBwdThreads / 32;
+    __shared__ TileOrder<TW, TH> s_order;
+    int n_units = p.units;
+    if constexpr (TILED) {
+        tile_order_init(s_order, lv, p.L);
+        n_units = (int)((unsigned)p.B * (unsigned)s_order.before[p.L] * (unsigned)p.H);
+    }
 
     const int lane = threadIdx.x % G;
     const int gid = threadIdx.x / G;
@@ -637,12 +703,12 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     if constexpr (DET) dscale = *p.det_scale;
 
 #if BXR_UNIT_REVERSE
-    for (int u = p.units - 1 - (int)blockIdx.x; u >= 0; u -= gridDim.x) {
+    for (int u = (TILED ? (int)blockIdx.x : n_units - 1 - (int)blockIdx.x); TILED ? (u < n_units) : (u >= 0); u += TILED ? (int)gridDim.x : -(int)gridDim.x) {
 #else
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 #endif
-        const long long row_raw = (long long)u * GROUPS + gid;
-        const bool ract = row_raw < p.rows;     // groups past the last row stay with their warp, doing nothing
+        const long long row_raw = TILED ? tile_order_row(s_order, lv, p, (unsigned)u, gid) : (long long)u * GROUPS + gid;
+        const bool ract = TILED ? (row_raw >= 0) : (row_raw < p.rows);     // groups without a row stay with their warp, doing nothing
         const long long row = ract ? row_raw : 0;
         const int head = (int)(row % p.H);
         const long long b = row / ((long long)p.H * p.Nq);

@@ -35,6 +35,7 @@ FLAG_PATH_WINDOW = 0x2
 FLAG_PATH_POINT = 0x4
 FLAG_STAGED = 0x8
 FLAG_PATH_TILE = 0x10
+FLAG_NO_TILE_ORDER = 0x20
 _PATH_FLAGS = 0               # tuning / testing override of the kernel family (see set_kernel_path)
 
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
@@ -58,10 +59,13 @@ def set_kernel_path(path: str = "auto"):
     "window" / "point": force one family where it applies (A/B benchmarking and tests);
     "staged" / "window-staged": the window forward with TMA-staged row operands and a pooled multi-level window
     (experiment, boxattn_staged.cuh; measured no faster than the plain window kernels);
-    "tile": the query-tile x value-tile kernels (boxattn_tile.cuh) whenever they apply (Nq == S, head_dim 32, P <= 16)."""
+    "tile": the query-tile x value-tile kernels (boxattn_tile.cuh) whenever they apply (Nq == S, head_dim 32, P <= 16);
+    "window-memory-order": the window kernels with work units in memory order (A/B of the tile-ordered units they use for
+    self-attention-shaped calls)."""
     global _PATH_FLAGS
     _PATH_FLAGS = {"auto": 0, "window": FLAG_PATH_WINDOW, "point": FLAG_PATH_POINT, "staged": FLAG_STAGED,
-                   "window-staged": FLAG_PATH_WINDOW | FLAG_STAGED, "tile": FLAG_PATH_TILE}[path]
+                   "window-staged": FLAG_PATH_WINDOW | FLAG_STAGED, "tile": FLAG_PATH_TILE,
+                   "window-memory-order": FLAG_NO_TILE_ORDER}[path]
 
 
 def last_launch_count() -> int:

@@ -77,6 +77,9 @@ typedef enum bxr_status {
 #define BXR_FLAG_PATH_TILE 0x10u     /* tuning/testing: query-tile x value-tile kernels (TMA-staged value halos in shared
                                        memory, boxattn_tile.cuh) whenever they apply (Nq == S, head_dim 32, P <= 16) */
 
+#define BXR_FLAG_NO_TILE_ORDER 0x20u /* tuning/testing: footprint-window kernels with work units in memory order even for
+                                       self-attention-shaped calls (Nq == S), where units are dealt as 2-D query tiles */
+
 typedef void* bxr_stream_t;   /* a cudaStream_t */
 typedef uint16_t bxr_bf16;    /* raw bfloat16 bits */
 
