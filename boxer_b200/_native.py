@@ -44,7 +44,7 @@ EXPORTS = (
     + [f"bxr_instance_weights_{d}_{dt}" for d in ("fwd", "bwd") for dt in ("f32", "f64")]
 )
 
-_lock = threading.Lock()
+_lock = threading.RLock()      # re-entrant: load_shim() loads the C-ABI library under it
 _lib = None
 
 
@@ -93,11 +93,84 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print("\n".join(logs))
         tmp = LIB_PATH + ".tmp"
-        link = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *[o for o, _ in procs]], capture_output=True, text=True)
+        # the soname lets the pybind shim's NEEDED entry resolve to the copy ctypes already loaded, wherever the tree lives
+        link = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xlinker", "-soname=libboxattn_b200.so",
+                               "-o", tmp, *[o for o, _ in procs]], capture_output=True, text=True)
         if link.returncode != 0:
             raise RuntimeError("link failed:\n" + link.stdout + link.stderr)
         os.replace(tmp, LIB_PATH)
         return LIB_PATH
+
+
+SHIM_NAME = "_boxattn_torch"
+SHIM_SOURCE = os.path.join(CSRC, "boxattn_torch.cpp")
+SHIM_PATH = os.path.join(LIB_DIR, SHIM_NAME + ".so")
+_shim = None
+_shim_tried = False
+
+
+def shim_is_stale() -> bool:
+    if not os.path.exists(SHIM_PATH):
+        return True
+    t = os.path.getmtime(SHIM_PATH)
+    return any(os.path.getmtime(d) > t for d in (SHIM_SOURCE, HEADER))
+
+
+def build_torch_shim(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/boxattn_torch.cpp (the pybind fast path over the same C ABI) into boxer_b200/_C/_boxattn_torch.so.
+    Host-only C++: needs g++ and the torch headers, no GPU.  The shim links against libboxattn_b200.so: load_shim() loads that
+    library first (its soname satisfies the shim's NEEDED entry); an $ORIGIN rpath covers a direct import."""
+    with _lock:
+        if not force and not shim_is_stale():
+            return SHIM_PATH
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("build libboxattn_b200.so first")
+        import shutil as _sh
+        from torch.utils.cpp_extension import load
+        bdir = os.path.join(os.environ.get("TMPDIR", "/tmp"), "boxattn_b200_shim_build")
+        os.makedirs(bdir, exist_ok=True)
+        os.environ.setdefault("MAX_JOBS", "4")
+        built = os.path.join(bdir, SHIM_NAME + ".so")
+        if os.path.exists(built):
+            os.remove(built)
+        try:
+            load(name=SHIM_NAME, sources=[SHIM_SOURCE], extra_include_paths=[os.path.join(ROOT, "include")],
+                 extra_cflags=["-O2"], extra_ldflags=[f"-L{LIB_DIR}", "-l:libboxattn_b200.so", "-Wl,-rpath,'$$ORIGIN'"],
+                 with_cuda=True, build_directory=bdir, is_python_module=False, verbose=verbose)
+        except OSError:
+            # cpp_extension tries to dlopen the result inside the build directory, where the $ORIGIN rpath does not
+            # find libboxattn_b200.so yet; the file itself is complete
+            if not os.path.exists(built):
+                raise
+        tmp = SHIM_PATH + ".tmp"
+        _sh.copy2(os.path.join(bdir, SHIM_NAME + ".so"), tmp)
+        os.replace(tmp, SHIM_PATH)
+        return SHIM_PATH
+
+
+def load_shim():
+    """The pybind fast path, or None (then ops.py uses ctypes on the same C ABI).  Never used with BOXER_B200_LIB set:
+    the shim is linked against the in-tree library."""
+    global _shim, _shim_tried
+    if _shim_tried:
+        return _shim
+    with _lock:
+        if not _shim_tried:
+            _shim_tried = True
+            if os.environ.get("BOXER_B200_LIB") or os.environ.get("BOXER_B200_NO_SHIM") or not os.path.exists(SHIM_PATH):
+                return None
+            try:
+                import importlib.util
+                load()                      # the C-ABI library first (one instance per process)
+                import torch  # noqa: F401
+                spec = importlib.util.spec_from_file_location(SHIM_NAME, SHIM_PATH)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                if mod.abi_version() == 1:
+                    _shim = mod
+            except Exception:               # a shim built against another torch: the ctypes route still works
+                _shim = None
+    return _shim
 
 
 def _declare(lib):

@@ -52,15 +52,12 @@ constexpr int kFwdThreads = BXR_FWD_THREADS, kFwdMinB = BXR_FWD_MINB;
 // the 72-register budget holds for the fp32 location-taking kernels with up to 2 points per lane (ptxas: 4 bytes of
 // spill); the fused-grid / softmax variants, 4 points per lane and the bf16 kernels (unpacking registers; r01x:
 // bf16 forward 3-6 % slower at 72) keep the 80-register budget (24 warps)
-// BXR_FWD_MINB_LPP2 (next-round A/B hook, default = BXR_FWD_MINB): resident CTAs of the two-levels-per-pass
-// kernels (2 x 2 grids), which measured 2 % faster at 6 x 128 threads / 80 registers (r02b: 0.0860 vs 0.0885 ms)
-#ifndef BXR_FWD_MINB_LPP2
-#define BXR_FWD_MINB_LPP2 BXR_FWD_MINB
-#endif
-constexpr int fwd_min_blocks(int vec, int ppl, bool fused, bool fp32, bool two_levels) {
+// (r02l: 6 instead of 7 resident CTAs for the two-levels-per-pass kernels of 2 x 2 grids measured no faster on a second
+// box -- 0.0885 vs 0.0874 ms -- and the hook was removed)
+constexpr int fwd_min_blocks(int vec, int ppl, bool fused, bool fp32, bool /*two_levels*/) {
     return vec > 4 ? 2 * (kThreads / kFwdThreads)
                    : ((fused || ppl > 2 || !fp32) ? 3 * (kThreads / kFwdThreads)
-                                                  : (two_levels ? BXR_FWD_MINB_LPP2 : kFwdMinB));
+                                                  : kFwdMinB);
 }
 constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 // Forward window walk from a slot table: after the scatter, the lanes of the level turn the dense window into
@@ -74,23 +71,37 @@ constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 #endif
 template <typename TV>
 struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD_TAB == 2 && !std::is_same<TV, float>::value); };
-// BXR_BWD_TAB (next-round A/B hook, default 0; written without a GPU at hand -- run the window tests on it first):
-// the backward walk from a slot table like the bf16 forward's.  One lane per slot writes (offset relative to the
-// lane's base pointers, float weight) after the scatter; an untouched slot carries a NaN weight.  The walk then
-// needs no row-wrap arithmetic, no flag read, no int -> float scaling per lane, and no group barrier before the
-// d totals overwrite the flag window (the flags are consumed when the table is built).
-#ifndef BXR_BWD_TAB
-#define BXR_BWD_TAB 0
+// BXR_FWD_CTAB: forward, wide footprints (the per-point mode).  Instead of broadcasting every point's tap from its owner
+// lane (6 shuffles + the corner arithmetic on all G lanes, per point), each lane writes the four corners of its own points
+// as (offset, weight) entries of the slot table and the group walks the 4 P entries exactly like a window's slots.
+// 0 off, 1 on for P <= 16 (the table holds 64 entries per group).
+#ifndef BXR_FWD_CTAB
+#define BXR_FWD_CTAB 1
 #endif
-// BXR_BASE_REGPAIR (next-round A/B hook, default 0): gather through a per-lane base pointer kept as an opaque
-// register pair, offsets relative to it -- one IMAD.WIDE per load; otherwise the compiler re-loads the tensor
-// base from the constant bank (LDC.64) in front of every load (seen in SASS, boxattn_window.cuh forward walk)
+// BXR_BWD_TAB: the backward walk from a slot table like the bf16 forward's.  0 off, 1 all types, 2 all but fp32 (default).
+// Measured r02l (K=4 encoder backward): bf16 0.4118 -> 0.3946 ms, fp32 0.3526 -> 0.3767 ms (as in the forward, the extra
+// shared-memory round trip per pass costs the fp32 kernel more than the saved instructions buy).  One lane per slot writes (offset relative to the
+// lane's base pointers, float weight) after the scatter.  The walk then
+// needs no row-wrap arithmetic, no flag read, no int -> float scaling per lane, and no group barrier before the
+// d totals overwrite the flag window (the flags are consumed when the table is built).  An untouched pixel is marked by
+// the offset kAbsent (not by its weight: non-finite weights must reach grad_value).
+#ifndef BXR_BWD_TAB
+#define BXR_BWD_TAB 2
+#endif
+// BXR_BASE_REGPAIR: gather through a per-lane base pointer kept as an opaque register pair, offsets relative to it -- one
+// IMAD.WIDE per load; otherwise the compiler re-loads the tensor base from the constant bank (LDC.64) in front of every
+// load (seen in SASS, forward walk).  Measured r02l: forward K=4 0.1779 -> 0.1745 ms, uniform 0.346 -> 0.335, bf16
+// 0.186 -> 0.1826; the two-levels-per-pass forward (2 x 2 grids) 0.0874 -> 0.0898 and the backward 0.3526 -> 0.3619 lose.
+// 0 off, 1 = forward kernels with one level per pass (default), 2 = everywhere (the r02l A/B build).
 #ifndef BXR_BASE_REGPAIR
-#define BXR_BASE_REGPAIR 0
+#define BXR_BASE_REGPAIR 1
 #endif
 // unroll factors of the per-point fallback loops: the walk is a chain of dependent gathers, unrolling lets the
 // compiler request the corner rows of several points before the first is used (A/B r01s: forward 1 -> 8:
 // 0.1846 -> 0.1794 ms, uniform 0.382 -> 0.362 ms; backward 1 -> 4: 0.365 -> 0.350 ms, 8 is worse there)
+#ifndef BXR_BWD_CTAB
+#define BXR_BWD_CTAB 1
+#endif
 #ifndef BXR_FB_UNROLL
 #define BXR_FB_UNROLL 8
 #endif
@@ -106,6 +117,8 @@ struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD
 #endif
 constexpr int kFbUnroll = BXR_FB_UNROLL;
 constexpr int kFbUnrollBwd = BXR_FB_UNROLL_BWD;
+// table entry of a pixel nobody touched / a corner outside the level (valid offsets stay below it: use_window())
+constexpr unsigned kAbsent = 0xffffffffu;
 // "no pixel touched yet" sentinel of the range reductions: with +-kNoPix in both ends the extent
 // max - min + 1 of an empty range is a large negative number that still fits an int (+-INT_MAX wrapped
 // around to 3, which sent rows without any in-range point through a 3 x 3 window of zeros)
@@ -372,8 +385,12 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];
     constexpr bool TAB = FwdSlotTable<TV>::value;
-    __shared__ __align__(16) uint2 s_tab[TAB ? GROUPS * kTabPitch : 2];
+    // corner entries of one level (4 per point) must fit the level's share of the table: decided by the geometry alone, so
+    // that an instantiation carries either the table walk or the shuffle walk for wide footprints, never both
+    constexpr bool CTAB = BXR_FWD_CTAB != 0 && 4 * SUB * PPL <= CAP;
+    __shared__ __align__(16) uint2 s_tab[(TAB || CTAB) ? GROUPS * kTabPitch : 2];
     load_levels(lv, p);
+    constexpr bool ctab = CTAB;
     // tile-ordered units: a warp (32 / G rows) is a tile line, the CTA a tile of (32 / G) x (warps) queries of one head
     constexpr int TW = 32 / G, TH = kFwdThreads / 32;
     __shared__ TileOrder<TW, TH> s_order;
@@ -389,8 +406,8 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
     const unsigned gm = group_mask<G>();
     int* gwin = s_win + gid * kWinPitch;
     int* win = gwin + sub * CAP;
-    uint2* gtab = s_tab + (TAB ? gid * kTabPitch : 0);
-    uint2* tab = gtab + (TAB ? sub * CAP : 0);
+    uint2* gtab = s_tab + ((TAB || CTAB) ? gid * kTabPitch : 0);
+    uint2* tab = gtab + ((TAB || CTAB) ? sub * CAP : 0);
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in lane chunks (VEC elements)
     const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -496,7 +513,27 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                     tab[ts] = make_uint2(tbase + y * trow + x * HDV, __float_as_uint(wv));
                 }
             }
-            if constexpr (TAB) __syncwarp();
+            // ---- B'': wide footprint: my points' corners as table entries (offset from the row's base, attn * bilinear weight)
+            if constexpr (CTAB) if (me.mode == 2) {
+                const unsigned tlev = (unsigned)lv.start[lmc] * HDV;
+#pragma unroll
+                for (int k = 0; k < PPL; ++k) {
+                    const int ptn = slane + k * SUB;
+                    if (ptn < p.P) {
+                        const LanePoint& t = pt[k];
+                        const float hx = 1.f - t.lx, hy = 1.f - t.ly;
+                        const bool vx0 = t.x0 >= 0, vx1 = t.x0 + 1 <= mw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= mh - 1;
+                        const unsigned c00 = tlev + (unsigned)(t.y0 * mw + t.x0) * HDV;      // wraps for -1; such corners get weight 0
+                        const float aw = t.inside ? t.aw : 0.f;
+                        uint4* e = reinterpret_cast<uint4*>(tab + ptn * 4);
+                        e[0] = make_uint4((vy0 && vx0) ? c00 : 0u, __float_as_uint((vy0 && vx0) ? hy * hx * aw : 0.f),
+                                          (vy0 && vx1) ? c00 + HDV : 0u, __float_as_uint((vy0 && vx1) ? hy * t.lx * aw : 0.f));
+                        e[1] = make_uint4((vy1 && vx0) ? c00 + (unsigned)mw * HDV : 0u, __float_as_uint((vy1 && vx0) ? t.ly * hx * aw : 0.f),
+                                          (vy1 && vx1) ? c00 + (unsigned)mw * HDV + HDV : 0u, __float_as_uint((vy1 && vx1) ? t.ly * t.lx * aw : 0.f));
+                    }
+                }
+            }
+            if constexpr (TAB || CTAB) __syncwarp();
 
             // ---- C: all G lanes walk the window(s) of this pass
 #pragma unroll
@@ -513,18 +550,15 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
                 const int lh = lv.h[l], lw = lv.w[l];
-#if BXR_BASE_REGPAIR
-                const typename V::Raw* vbase = static_cast<const typename V::Raw*>(value16) + vrow;
-                asm volatile("" : "+l"(vbase));
-                const unsigned vlev = (unsigned)lv.start[l] * HDV;
-#else
-                const void* vbase = value16;
-                const unsigned vlev = vrow + (unsigned)lv.start[l] * HDV;
-#endif
-                if (TAB && w.mode == 1) {
-                    // one row load per unique pixel, four table entries (two 16-byte shared loads) at a time
+                constexpr bool REGPAIR = BXR_BASE_REGPAIR == 2 || (BXR_BASE_REGPAIR == 1 && LPP == 1);
+                const typename V::Raw* vbase = static_cast<const typename V::Raw*>(value16) + (REGPAIR ? vrow : 0u);
+                if constexpr (REGPAIR) asm volatile("" : "+l"(vbase));
+                const unsigned vlev = (REGPAIR ? 0u : vrow) + (unsigned)lv.start[l] * HDV;
+                if ((TAB && w.mode == 1) || (ctab && w.mode == 2)) {
+                    // one row load per unique pixel (window) or per corner (wide footprint), four table entries (two
+                    // 16-byte shared loads) at a time
                     const uint2* ct = gtab + sl * CAP;
-                    const int wq_n = w.nx * w.ny;
+                    const int wq_n = w.mode == 1 ? w.nx * w.ny : 4 * p.P;
                     // per-lane base pointer in registers: the table offsets are the same for all lanes of the group
                     const typename V::Raw* vlane = static_cast<const typename V::Raw*>(value16) + vrow;
                     asm volatile("" : "+l"(vlane));      // keep it a register pair: one IMAD.WIDE per load, no re-derivation
@@ -579,7 +613,7 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                             }
                         }
                     }
-                } else {
+                } else if constexpr (!CTAB) {
                     // per-point fallback: the owner lane broadcasts its tap
 #pragma unroll
                     for (int k = 0; k < PPL; ++k) {
@@ -671,8 +705,16 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];     // pixel weights W[pix], fixed point
     __shared__ __align__(16) float s_dot[GROUPS * kWinPitch];   // "touched" flag, then d[pix] = <grad_out, value[pix]>
-    constexpr bool TABB = (BXR_BWD_TAB != 0) && G >= 8;     // G = 4: 64 groups per CTA, the table would not fit 48 KB
-    __shared__ __align__(16) uint2 s_tab[TABB ? GROUPS * kTabPitch : 2];
+    constexpr bool TABB = (BXR_BWD_TAB == 1 || (BXR_BWD_TAB == 2 && !std::is_same<TV, float>::value)) && G >= 8;     // G = 4: 64 groups per CTA, the table would not fit 48 KB
+    // BXR_BWD_CTAB: wide footprints (the per-point mode) as a window whose slots are the 4 P corners: each lane writes its
+    // points' corners as table entries, the group walks them like a window's slots (d per corner by transpose reduction,
+    // one scatter per corner) and every lane finishes its own points from the d entries -- instead of 6 broadcast shuffles
+    // and 4 full group reductions per point.  Decided by the geometry, like the forward's.
+    // Measured r02n (K=4 encoder backward, corner table vs shuffle walk): trained-like boxes 0.784 -> 0.636 ms, init-state
+    // boxes 0.348 -> 0.346, uniform points 1.095 -> 1.108 (bound by the L2 atomics either way); the two-levels-per-pass
+    // kernels of 2 x 2 grids lose 3 % (0.1855 -> 0.191) and keep the shuffle walk.
+    constexpr bool CTABB = BXR_BWD_CTAB != 0 && G >= 8 && LPP == 1 && 4 * SUB * PPL <= CAP;
+    __shared__ __align__(16) uint2 s_tab[(TABB || CTABB) ? GROUPS * kTabPitch : 2];
     load_levels(lv, p);
     constexpr int TW = 32 / G, TH = kBwdThreads / 32;
     __shared__ TileOrder<TW, TH> s_order;
@@ -690,8 +732,8 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     float* gdot = s_dot + gid * kWinPitch;
     int* win = gwin + sub * CAP;
     float* dot = gdot + sub * CAP;
-    uint2* gtab = s_tab + (TABB ? gid * kTabPitch : 0);
-    uint2* tab = gtab + (TABB ? sub * CAP : 0);
+    uint2* gtab = s_tab + ((TABB || CTABB) ? gid * kTabPitch : 0);
+    uint2* tab = gtab + ((TABB || CTABB) ? sub * CAP : 0);
     const unsigned HDV = (unsigned)(p.H * p.D) / VEC;      // pixel pitch in lane chunks (VEC elements)
     const void* __restrict__ value16 = p.value;   // indexed in lane-chunk units by V::load16
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
@@ -789,11 +831,30 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                 for (int ts = slane; ts < nq4; ts += SUB) {
                     const unsigned y = ((unsigned)ts * rcp) >> 16;
                     const unsigned x = (unsigned)ts - y * (unsigned)me.nx;
-                    const float wv = dot[ts] != 0.f ? (float)win[ts] * inv_scale : __int_as_float(0x7fc00000);
-                    tab[ts] = make_uint2(tbase + y * trow + x * HDV, __float_as_uint(wv));
+                    const bool touched = dot[ts] != 0.f;
+                    tab[ts] = make_uint2(touched ? tbase + y * trow + x * HDV : kAbsent, __float_as_uint(touched ? (float)win[ts] * inv_scale : 0.f));
                 }
             }
-            if constexpr (TABB) __syncwarp();
+            // B'': wide footprint: my points' corners as table entries (offset, attn * bilinear weight; NaN = no such corner)
+            if constexpr (CTABB) if (me.mode == 2) {
+                const unsigned tlev = (unsigned)lv.start[lmc] * HDV;
+#pragma unroll
+                for (int k = 0; k < PPL; ++k) {
+                    const int ptn = slane + k * SUB;
+                    if (ptn < p.P) {
+                        const LanePoint& t = pt[k];
+                        const float hx = 1.f - t.lx, hy = 1.f - t.ly;
+                        const bool vx0 = t.inside && t.x0 >= 0, vx1 = t.inside && t.x0 + 1 <= mw - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= mh - 1;
+                        const unsigned c00 = tlev + (unsigned)(t.y0 * mw + t.x0) * HDV;      // wraps for -1; such corners are marked absent
+                        uint4* e = reinterpret_cast<uint4*>(tab + ptn * 4);
+                        e[0] = make_uint4((vy0 && vx0) ? c00 : kAbsent, __float_as_uint((vy0 && vx0) ? hy * hx * t.aw : 0.f),
+                                          (vy0 && vx1) ? c00 + HDV : kAbsent, __float_as_uint((vy0 && vx1) ? hy * t.lx * t.aw : 0.f));
+                        e[1] = make_uint4((vy1 && vx0) ? c00 + (unsigned)mw * HDV : kAbsent, __float_as_uint((vy1 && vx0) ? t.ly * hx * t.aw : 0.f),
+                                          (vy1 && vx1) ? c00 + (unsigned)mw * HDV + HDV : kAbsent, __float_as_uint((vy1 && vx1) ? t.ly * t.lx * t.aw : 0.f));
+                    }
+                }
+            }
+            if constexpr (TABB || CTABB) __syncwarp();
 
             // C: all G lanes walk the window(s) of this pass
 #pragma unroll
@@ -810,7 +871,7 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
                 const int lh = lv.h[l], lw = lv.w[l];
-#if BXR_BASE_REGPAIR
+#if BXR_BASE_REGPAIR == 2
                 const typename V::Raw* vptr = static_cast<const typename V::Raw*>(value16) + vbase;
                 ACC* gptr = gacc + (size_t)vbase * VEC;
                 asm volatile("" : "+l"(vptr), "+l"(gptr));
@@ -820,10 +881,10 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                 ACC* gptr = gacc;
                 const unsigned lbase = vbase + (unsigned)lv.start[l] * HDV;
 #endif
-                if (TABB && w.mode == 1) {
+                if ((TABB && w.mode == 1) || (CTABB && w.mode == 2)) {
                     const uint2* ct = gtab + sl * CAP;
                     float* cdot = gdot + sl * CAP;
-                    const int wq_n = w.nx * w.ny;
+                    const int wq_n = w.mode == 1 ? w.nx * w.ny : 4 * p.P;
                     // lane base pointers as opaque register pairs; the table offsets are shared by the group's lanes
                     const typename V::Raw* tvp = static_cast<const typename V::Raw*>(value16) + vbase;
                     ACC* tgp = gacc + (size_t)vbase * VEC;
@@ -836,7 +897,7 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                         float v[4][VEC];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (tw[j] == tw[j]) {      // touched (an untouched slot carries NaN)
+                            if (to[j] != kAbsent) {      // a touched pixel / an existing corner
                                 V::load16(tvp, to[j], v[j]);
                             } else {
 #pragma unroll
@@ -850,7 +911,7 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
                             dsum[j] = t;
-                            if (fabsf(tw[j]) > 0.f) scatter_row<ACC, VEC>(tgp + (size_t)to[j] * VEC, go, tw[j], dscale);   // false for NaN
+                            if (to[j] != kAbsent && tw[j] != 0.f) scatter_row<ACC, VEC>(tgp + (size_t)to[j] * VEC, go, tw[j], dscale);   // NaN weights propagate
                         }
                         float total;
                         const int mine = reduce4<G>(dsum, total, lane, gm);
@@ -902,7 +963,7 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                         __syncwarp(gm);                                        // every lane has consumed the flags of these slots
                         cdot[q + mine] = total;                                // lanes sharing an index write the same value
                     }
-                } else {
+                } else if constexpr (!CTABB) {
                     // per-point fallback (window too large, or non-finite weights)
 #pragma unroll
                     for (int k = 0; k < PPL; ++k) {
@@ -962,6 +1023,20 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                         g_a[k] = hy * hx * d00 + hy * lx * d01 + ly * hx * d10 + ly * lx * d11;
                         g_x[k] = (float)mw * pt[k].aw * (hy * (d01 - d00) + ly * (d11 - d10));
                         g_y[k] = (float)mh * pt[k].aw * (hx * (d10 - d00) + lx * (d11 - d01));
+                    }
+                }
+            }
+            if constexpr (CTABB) if (me.mode == 2) {
+                // D': finish own points from the d entries of their four corners (absent corners hold 0)
+#pragma unroll
+                for (int k = 0; k < PPL; ++k) {
+                    const int ptn = slane + k * SUB;
+                    if (ptn < p.P && pt[k].inside) {
+                        const float4 d = *reinterpret_cast<const float4*>(dot + ptn * 4);
+                        const float lx = pt[k].lx, ly = pt[k].ly, hx = 1.f - lx, hy = 1.f - ly;
+                        g_a[k] = hy * hx * d.x + hy * lx * d.y + ly * hx * d.z + ly * lx * d.w;
+                        g_x[k] = (float)mw * pt[k].aw * (hy * (d.y - d.x) + ly * (d.w - d.z));
+                        g_y[k] = (float)mh * pt[k].aw * (hx * (d.z - d.x) + lx * (d.w - d.y));
                     }
                 }
             }

@@ -16,7 +16,8 @@ def time_call(fn, reps=30):
 
 res = {"lib": os.path.basename(_native.LIB_PATH)}
 for name, w in (("K4_box", W.coco_encoder(K=4, device="cuda")), ("K4_uni", W.coco_encoder(K=4, dist="uniform", device="cuda")),
-                ("K2_box", W.coco_encoder(K=2, device="cuda"))):
+                ("K2_box", W.coco_encoder(K=2, device="cuda")), ("K4_trained", W.coco_encoder(K=4, dist="trained", device="cuda")),
+                ("K2_uni", W.coco_encoder(K=2, dist="uniform", device="cuda"))):
     go = torch.randn(1, w.value.shape[1], 256, device="cuda")
     a = (w.value, w.shapes, w.level_start, w.loc, w.weights[0])
     res[name] = (round(time_call(lambda: ops.box_attn_forward(*a, 64)), 4), round(time_call(lambda: ops.box_attn_backward(*a, go, 64)), 4))

@@ -290,3 +290,24 @@ def test_slot_table_index_arithmetic():
     k = 0x3FFFFFFF
     for hi in (1, 10 ** 6):                      # extent of an empty range: max - min + 1 with the clamps applied
         assert -(2 ** 31) <= min(-k, hi - 1) - max(k, 0) + 1 < 0
+
+
+def test_torch_shim_loads_and_defers_to_python_for_unusual_inputs():
+    """boxer_b200/_C/_boxattn_torch.so (csrc/boxattn_torch.cpp): the pybind fast path over the same C ABI.  Without a GPU
+    only its loading and its "not the plain case -> None" contract can be exercised."""
+    from boxer_b200 import _native
+    if not os.path.exists(_native.SHIM_PATH):
+        pytest.skip("shim not built")
+    shim = _native.load_shim()
+    assert shim is not None and shim.abi_version() == 1
+    for f in ("box_attn_forward", "box_attn_backward", "instance_attn_forward", "instance_attn_backward"):
+        assert callable(getattr(shim, f))
+    v = torch.zeros(1, 4, 2, 32)
+    sh = torch.tensor([[2, 2]])
+    ls = torch.tensor([0])
+    loc = torch.zeros(1, 3, 2, 1, 4, 2)
+    w = torch.zeros(1, 3, 2, 1, 4)
+    assert shim.box_attn_forward(v, sh, ls, loc, w, 64, 0) is None          # CPU tensors: the Python route raises the error
+    import boxer_b200
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        boxer_b200.ops.box_attn_forward(v, sh, ls, loc, w, 64)
