@@ -194,7 +194,17 @@ def _workspace(lib, value, flags):
 # Fast path: the pybind shim (csrc/boxattn_torch.cpp) validates, allocates and calls the same C-ABI entry points in C++
 # (~6 us per call instead of ~15: decoder-sized calls are launch-latency bound).  It returns None for anything but the
 # plain case, and then -- or when the shim is not built -- the Python route below runs, with its diagnostics.
-_SHIM = _native.load_shim()
+_SHIM = None
+_SHIM_READY = False
+
+
+def _shim():
+    """Resolved on the first op call (importing the package must not dlopen anything)."""
+    global _SHIM, _SHIM_READY
+    if not _SHIM_READY:
+        _SHIM = _native.load_shim()
+        _SHIM_READY = True
+    return _SHIM
 
 
 def _bwd_flags():
@@ -202,7 +212,7 @@ def _bwd_flags():
 
 
 def box_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64):
-    if _SHIM is not None:
+    if (_SHIM if _SHIM_READY else _shim()) is not None:
         try:
             r = _SHIM.box_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, _PATH_FLAGS)
         except TypeError:
@@ -224,7 +234,7 @@ def box_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, att
 
 
 def box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step=64):
-    if _SHIM is not None:
+    if (_SHIM if _SHIM_READY else _shim()) is not None:
         try:
             r = _SHIM.box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                                         im2col_step, _bwd_flags())
@@ -258,7 +268,7 @@ def box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, at
 # ------------------------------------------------------------- instance op
 def instance_attn_forward(value, spatial_shapes, level_start_index, sampling_loc,
                           spatial_attn_weight, level_attn_weight, im2col_step=64):
-    if _SHIM is not None:
+    if (_SHIM if _SHIM_READY else _shim()) is not None:
         try:
             r = _SHIM.instance_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, spatial_attn_weight,
                                             level_attn_weight, im2col_step, _PATH_FLAGS)
@@ -284,7 +294,7 @@ def instance_attn_forward(value, spatial_shapes, level_start_index, sampling_loc
 
 def instance_attn_backward(value, spatial_shapes, level_start_index, sampling_loc,
                            spatial_attn_weight, level_attn_weight, grad_output, grad_mask_output, im2col_step=64):
-    if _SHIM is not None:
+    if (_SHIM if _SHIM_READY else _shim()) is not None:
         try:
             r = _SHIM.instance_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, spatial_attn_weight,
                                              level_attn_weight, grad_output, grad_mask_output, im2col_step, _bwd_flags())
