@@ -81,6 +81,9 @@ int sm_count() {
     return cache[dev];
 }
 
+#ifndef BXR_INST_TAB_BWD
+#define BXR_INST_TAB_BWD 0
+#endif
 #ifndef BXR_TILE_DEFAULT
 #define BXR_TILE_DEFAULT 0
 #endif
@@ -467,12 +470,23 @@ void choose_chunk_split(AttnParams& p, int G) {
 template <typename TV, int G>
 int fwd_inst_own(AttnParams& p, cudaStream_t st) {
     choose_chunk_split(p, G);
+    // taps through the shared-memory table for fp32 (r02q: K=14 0.118 -> 0.095 ms, K=28 0.427 -> 0.344); the bf16 forward
+    // (8 channels per lane: FMA-bound) measured 2-5 % slower with it and keeps the shuffle broadcast
+#if BXR_INST_TAB
+    if constexpr (sizeof(TV) == 4) return launch_units<inst_fwd_tab_kernel<TV, G, kInstLevels>>(p, st, "inst_fwd_tab_kernel");
+#endif
     return launch_units<inst_fwd_own_kernel<TV, G, kInstLevels>>(p, st, "inst_fwd_own_kernel");
 }
 template <typename TV, int G, typename ACC>
 int bwd_inst_own(AttnParams& p, cudaStream_t st) {
     choose_chunk_split(p, G);
+    // the table / two-dots-per-corner backward measured SLOWER than the owner-tap one (r02q: fp32 K=14 0.289 -> 0.297 ms,
+    // bf16 0.284 -> 0.310): it is compiled only with BXR_INST_TAB_BWD=1
+#if BXR_INST_TAB_BWD
+    return launch_units<inst_bwd_tab_kernel<TV, G, kInstLevels, ACC>>(p, st, "inst_bwd_tab_kernel");
+#else
     return launch_units<inst_bwd_own_kernel<TV, G, kInstLevels, ACC>>(p, st, "inst_bwd_own_kernel");
+#endif
 }
 
 void fill_sizes(AttnParams& p, int B, int S, int H, int D, int L, int Nq, int P) {

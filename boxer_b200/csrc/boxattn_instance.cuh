@@ -332,4 +332,307 @@ __global__ void __launch_bounds__(kThreads, 2) inst_bwd_own_kernel(const AttnPar
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Round 2: the same two kernels with the taps in a shared-memory table instead of shuffles, and the backward's four
+// per-point sums rebuilt from two dot products per corner.
+//
+// The owner-tap kernels above broadcast every (point, level) tap with 7 shuffles and then ALL G lanes redo the corner
+// arithmetic (validity, offsets, weights) -- ~32 of the ~64 (forward) / ~150 (backward) instructions a (point, level)
+// costs.  Here the owner lane does that arithmetic once and writes, per level, {4 corner offsets (kAbsent: no such
+// corner), lx, ly, spatial_w, level_w} = 32 bytes to the group's table; the walk reads them back with two 16-byte
+// shared loads.  The backward no longer forms val / dval-dx / dval-dy per channel (18 FMAs per channel and level): with
+//     a_c = <grad_out, v_c>,  b_c = <grad_mask[p], v_c>          (two dot products per corner, 8 FMAs per channel and level)
+// everything it needs is linear in them:
+//     d spatial_w = sum_c cw_c a_c,   d level_w = sum_c cw_c b_c,   t_c = <top_grad, v_c> = sw a_c + lw b_c,
+//     d x = W (hy (t_1 - t_0) + ly (t_3 - t_2)),   d y = H (hx (t_2 - t_0) + lx (t_3 - t_1))
+// (instance_attn_kernel.cuh:139-186, re-associated).  The 8 partials are summed over the group's lanes with two 4-slot
+// transpose reductions, parked in shared memory, and the owner lane of the point finishes them.
+#ifndef BXR_INST_TAB
+#define BXR_INST_TAB 1
+#endif
+
+struct InstTap {
+    uint4 off;       // value offsets of the four corners in lane-chunk units, relative to the row's base; kAbsent = none
+    float4 f;        // lx, ly, spatial_w, level_w
+};
+
+__device__ __forceinline__ void inst_write_tap(InstTap* dst, const LanePoint& t, float lw_, unsigned lbase, int lh, int lwid, unsigned HDV) {
+    const bool vx0 = t.inside && t.x0 >= 0, vx1 = t.inside && t.x0 + 1 <= lwid - 1, vy0 = t.y0 >= 0, vy1 = t.y0 + 1 <= lh - 1;
+    const unsigned c00 = lbase + (unsigned)(t.y0 * lwid + t.x0) * HDV;       // wraps for -1; such corners are absent
+    InstTap e;
+    e.off = make_uint4((vy0 && vx0) ? c00 : kAbsent, (vy0 && vx1) ? c00 + HDV : kAbsent,
+                       (vy1 && vx0) ? c00 + (unsigned)lwid * HDV : kAbsent, (vy1 && vx1) ? c00 + (unsigned)lwid * HDV + HDV : kAbsent);
+    e.f = make_float4(t.lx, t.ly, t.aw, lw_);
+    *dst = e;
+}
+
+template <typename TV, int G, int LB>
+__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_INST_FWD_MINB_F32) inst_fwd_tab_kernel(const AttnParams p) {
+    using V = Vec16<TV>;
+    constexpr int VEC = V::VEC;
+    constexpr int LG = BXR_INST_LG;
+    static_assert(LB % LG == 0, "level batches must tile LB");
+    constexpr int GROUPS = kThreads / G;
+    __shared__ LevelTable lv;
+    __shared__ float s_red[kThreads * VEC];
+    __shared__ __align__(16) InstTap s_tap[kThreads * LB];        // [group][point of the chunk][level]
+    load_levels(lv, p);
+
+    const int lane = threadIdx.x % G;
+    const int gid = threadIdx.x / G;
+    const unsigned gm = group_mask<G>();       // the table is per group: its barriers involve the group's lanes only
+    const int nsplit = 1 << p.nsplit_log2;
+    const int rows_per_unit = GROUPS >> p.nsplit_log2;
+    const int r_local = gid >> p.nsplit_log2;
+    const int split = gid & (nsplit - 1);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;
+    const long long HD = (long long)p.H * p.D;
+    const float* __restrict__ loc = static_cast<const float*>(p.loc);
+    const float* __restrict__ w0 = static_cast<const float*>(p.w0);
+    const float* __restrict__ w1 = static_cast<const float*>(p.w1);
+    const int nchunks = (p.P + G - 1) / G;
+    InstTap* gtap = s_tap + gid * G * LB;
+
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const long long row = (long long)u * rows_per_unit + r_local;
+        const bool row_ok = row < p.rows;
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+        if (row_ok) {
+            const int head = (int)(row % p.H);
+            const long long bq = row / p.H;
+            const long long b = bq / p.Nq;
+            const typename V::Raw* vlane = static_cast<const typename V::Raw*>(p.value) + (size_t)(b * p.S * HDV + head * G + lane);
+            const float* loc_row = loc + row * p.LP * 2;
+            const float* sw_row = w0 + row * p.LP;
+            const float* lw_row = w1 + row * p.LP;
+            TV* mrow = static_cast<TV*>(p.mask_out) + (bq * p.P * HD + (long long)head * p.D + lane * VEC);
+
+            for (int c = split; c < nchunks; c += nsplit) {
+                const int p0 = c * G;
+                const int pm = p0 + lane;
+                // ---- my point's taps for every level, once, into the group's table
+                __syncwarp(gm);                    // the previous chunk's entries have been read
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    if (l < p.L) {
+                        const LanePoint t = lane_point(loc_row + l * p.P * 2, sw_row + l * p.P, pm, p.P, lv.h[l], lv.w[l]);
+                        const float lwv = pm < p.P ? __ldg(lw_row + l * p.P + pm) : 0.f;
+                        inst_write_tap(gtap + lane * LB + l, t, lwv, (unsigned)lv.start[l] * HDV, lv.h[l], lv.w[l], HDV);
+                    }
+                }
+                __syncwarp(gm);
+                const int n_here = min(G, p.P - p0);
+#pragma unroll 1
+                for (int o = 0; o < n_here; ++o) {
+                    float macc[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) macc[i] = 0.f;
+#pragma unroll
+                    for (int l0 = 0; l0 < LB; l0 += LG) {
+                        if (l0 >= p.L) break;
+                        typename V::Raw raw[LG][4];
+                        float4 f[LG];
+#pragma unroll
+                        for (int j = 0; j < LG; ++j) {
+                            const int l = l0 + j;
+                            InstTap t;
+                            if (l < p.L) {
+                                t = gtap[o * LB + l];
+                            } else {
+                                t.off = make_uint4(kAbsent, kAbsent, kAbsent, kAbsent);
+                                t.f = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            f[j] = t.f;
+                            const unsigned off[4] = {t.off.x, t.off.y, t.off.z, t.off.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                raw[j][k] = V::zero_raw();
+                                if (off[k] != kAbsent) raw[j][k] = __ldg(vlane + off[k]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < LG; ++j) {
+                            const float lx = f[j].x, ly = f[j].y, hx = 1.f - lx, hy = 1.f - ly;
+                            const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+                            float v[4][VEC];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) V::unpack_raw(raw[j][k], v[k]);
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) {
+                                const float val = cw[0] * v[0][i] + cw[1] * v[1][i] + cw[2] * v[2][i] + cw[3] * v[3][i];
+                                acc[i] += val * f[j].z;       // instance_attn_kernel.cuh:354
+                                macc[i] += val * f[j].w;      // :355
+                            }
+                        }
+                    }
+                    V::store(mrow + (long long)(p0 + o) * HD, macc);
+                }
+            }
+        }
+
+        TV* orow = static_cast<TV*>(p.out) + (row * p.D + lane * VEC);
+        if (nsplit == 1) {
+            if (row_ok) V::store(orow, acc);
+        } else {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s_red[threadIdx.x * VEC + i] = acc[i];
+            __syncthreads();
+            if (split == 0 && row_ok) {
+                for (int s = 1; s < nsplit; ++s)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[i] += s_red[(threadIdx.x + s * G) * VEC + i];
+                V::store(orow, acc);
+            }
+        }
+    }
+}
+
+template <typename TV, int G, int LB, typename ACC>
+__global__ void __launch_bounds__(kThreads, 2) inst_bwd_tab_kernel(const AttnParams p) {
+    using V = Vec16<TV>;
+    constexpr int VEC = V::VEC;
+    constexpr int GROUPS = kThreads / G;
+    constexpr bool DET = sizeof(ACC) == 8;
+    static_assert(G == 4 || G == 8 || G == 16, "transpose reduction");
+    __shared__ LevelTable lv;
+    __shared__ __align__(16) InstTap s_tap[kThreads * LB];
+    __shared__ __align__(16) float s_sum[GROUPS * LB * 8];        // [group][level][a_0..a_3, b_0..b_3] of the current point
+    load_levels(lv, p);
+
+    const int lane = threadIdx.x % G;
+    const int gid = threadIdx.x / G;
+    const unsigned gm = group_mask<G>();
+    const int nsplit = 1 << p.nsplit_log2;
+    const int rows_per_unit = GROUPS >> p.nsplit_log2;
+    const int r_local = gid >> p.nsplit_log2;
+    const int split = gid & (nsplit - 1);
+    const unsigned HDV = (unsigned)(p.H * p.D) / VEC;
+    const long long HD = (long long)p.H * p.D;
+    const float* __restrict__ loc = static_cast<const float*>(p.loc);
+    const float* __restrict__ w0 = static_cast<const float*>(p.w0);
+    const float* __restrict__ w1 = static_cast<const float*>(p.w1);
+    ACC* __restrict__ gacc = static_cast<ACC*>(p.grad_value_acc);
+    float* __restrict__ grad_loc = static_cast<float*>(p.grad_loc);
+    float* __restrict__ grad_w0 = static_cast<float*>(p.grad_w0);
+    float* __restrict__ grad_w1 = static_cast<float*>(p.grad_w1);
+    const int nchunks = (p.P + G - 1) / G;
+    InstTap* gtap = s_tap + gid * G * LB;
+    float* gsum_ = s_sum + gid * LB * 8;
+    float dscale = 1.f;
+    if constexpr (DET) dscale = *p.det_scale;
+
+    // (barriers and reductions use the group's mask: the groups of a warp walk different chunk ranges when a row's chunks
+    // are split over groups; rows past the end are carried along inactive)
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const long long row_raw = (long long)u * rows_per_unit + r_local;
+        const bool row_ok = row_raw < p.rows;
+        const long long row = row_ok ? row_raw : 0;
+        const int head = (int)(row % p.H);
+        const long long bq = row / p.H;
+        const long long b = bq / p.Nq;
+        const size_t vrow = (size_t)(b * p.S * HDV + head * G + lane);
+        const typename V::Raw* vlane = static_cast<const typename V::Raw*>(p.value) + vrow;
+        ACC* glane = gacc + vrow * VEC;
+        const float* loc_row = loc + row * p.LP * 2;
+        const float* sw_row = w0 + row * p.LP;
+        const float* lw_row = w1 + row * p.LP;
+        const TV* gmrow = static_cast<const TV*>(p.grad_mask) + (bq * p.P * HD + (long long)head * p.D + lane * VEC);
+        float go[VEC];
+        V::load(static_cast<const TV*>(p.grad_out) + (row * p.D + lane * VEC), go);
+
+        for (int c = split; c < nchunks; c += nsplit) {
+            const int p0 = c * G;
+            const int pm = p0 + lane;
+            float r_s[LB], r_l[LB], r_x[LB], r_y[LB];      // my point's gradients, per level
+            __syncwarp(gm);
+#pragma unroll
+            for (int l = 0; l < LB; ++l) {
+                r_s[l] = r_l[l] = r_x[l] = r_y[l] = 0.f;
+                if (l < p.L) {
+                    const LanePoint t = lane_point(loc_row + l * p.P * 2, sw_row + l * p.P, row_ok ? pm : p.P, p.P, lv.h[l], lv.w[l]);
+                    const float lwv = (row_ok && pm < p.P) ? __ldg(lw_row + l * p.P + pm) : 0.f;
+                    inst_write_tap(gtap + lane * LB + l, t, lwv, (unsigned)lv.start[l] * HDV, lv.h[l], lv.w[l], HDV);
+                }
+            }
+            __syncwarp(gm);
+            const int n_here = min(G, p.P - p0);
+            const typename V::Raw* gmraw = reinterpret_cast<const typename V::Raw*>(gmrow);
+            const long long gm_pitch = HD / VEC;
+            typename V::Raw gm_next = __ldg(gmraw + (long long)p0 * gm_pitch);
+#pragma unroll 1
+            for (int o = 0; o < n_here; ++o) {
+                float gmv[VEC];
+                V::unpack_raw(gm_next, gmv);
+                if (o + 1 < n_here) gm_next = __ldg(gmraw + (long long)(p0 + o + 1) * gm_pitch);
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    if (l >= p.L) break;
+                    const InstTap t = gtap[o * LB + l];
+                    const unsigned off[4] = {t.off.x, t.off.y, t.off.z, t.off.w};
+                    typename V::Raw raw[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        raw[k] = V::zero_raw();
+                        if (off[k] != kAbsent) raw[k] = __ldg(vlane + off[k]);
+                    }
+                    const float lx = t.f.x, ly = t.f.y, hx = 1.f - lx, hy = 1.f - ly;
+                    const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+                    float tg[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) tg[i] = go[i] * t.f.z + gmv[i] * t.f.w;    // instance_attn_kernel.cuh:139
+                    float a[4], bb[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float v[VEC];
+                        V::unpack_raw(raw[k], v);
+                        float sa = 0.f, sb = 0.f;
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) { sa += go[i] * v[i]; sb += gmv[i] * v[i]; }
+                        a[k] = sa; bb[k] = sb;
+                        if (row_ok && off[k] != kAbsent) scatter_row<ACC, VEC>(glane + (size_t)off[k] * VEC, tg, cw[k], dscale);
+                    }
+                    float ta, tb;
+                    const int ia = reduce4<G>(a, ta, lane, gm);
+                    reduce4<G>(bb, tb, lane, gm);
+                    gsum_[l * 8 + ia] = ta;             // lanes holding the same index hold the same total
+                    gsum_[l * 8 + 4 + ia] = tb;
+                }
+                __syncwarp(gm);
+                if (lane == o) {
+#pragma unroll
+                    for (int l = 0; l < LB; ++l) {
+                        if (l < p.L) {
+                            const float4 A = *reinterpret_cast<const float4*>(gsum_ + l * 8);
+                            const float4 Bv = *reinterpret_cast<const float4*>(gsum_ + l * 8 + 4);
+                            const InstTap t = gtap[o * LB + l];
+                            const float lx = t.f.x, ly = t.f.y, hx = 1.f - lx, hy = 1.f - ly, sw = t.f.z, lw_ = t.f.w;
+                            r_s[l] = hy * hx * A.x + hy * lx * A.y + ly * hx * A.z + ly * lx * A.w;      // :183
+                            r_l[l] = hy * hx * Bv.x + hy * lx * Bv.y + ly * hx * Bv.z + ly * lx * Bv.w;  // :184
+                            const float t0 = sw * A.x + lw_ * Bv.x, t1 = sw * A.y + lw_ * Bv.y, t2 = sw * A.z + lw_ * Bv.z, t3 = sw * A.w + lw_ * Bv.w;
+                            r_x[l] = (float)lv.w[l] * (hy * (t1 - t0) + ly * (t3 - t2));
+                            r_y[l] = (float)lv.h[l] * (hx * (t2 - t0) + lx * (t3 - t1));
+                        }
+                    }
+                }
+                __syncwarp(gm);      // the sums are overwritten by the next point
+            }
+            if (row_ok && pm < p.P) {
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    if (l < p.L) {
+                        const long long s = row * p.LP + (long long)l * p.P + pm;
+                        grad_w0[s] = r_s[l];
+                        grad_w1[s] = r_l[l];
+                        reinterpret_cast<float2*>(grad_loc)[s] = make_float2(r_x[l], r_y[l]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace bxr
