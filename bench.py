@@ -13,10 +13,17 @@ Printed (rank 0, ONE JSON line on stdout):
   e2e        same metric through the public API (BoxAttnFunction.apply + backward) with HOST
              (pinned) inputs: H2D of value/loc/weights/grad_out and D2H of out + all gradients
              inside the timed region
-  roofline   dominant kernel (backward) : algorithmic bytes / its CUDA-event time
-             vs the measured HBM copy bandwidth of MEASURED_PEAKS.json; roofline_fwd likewise
+  roofline   dominant kernel (backward) : algorithmic bytes (a no-reuse model) / its CUDA-event
+             time vs the measured HBM copy bandwidth of MEASURED_PEAKS.json; roofline_fwd likewise
+  roofline_compulsory  what can physically be held against HBM: compulsory bytes (inputs read once, outputs written
+             once) and ncu-measured DRAM bytes over the same kernel times
+  trained_like_locations / uniform_locations   the same sizes with the two other location distributions
+  reference_cuda  the reference's own CUDA kernels (oracle/_ref) at this config, timed in a subprocess
+  per_rank_ms_per_step  min / median / max over ranks of the timed regions
   cpu_baseline  the reference's pure-PyTorch grid_sample formulation (oracle/plain.py) on the
-             host CPU, all threads, on a bounded sample of the same workload
+             host CPU, all threads, full config, median of 3 passes
+--variants adds (stderr + gpurun_out/variants.json): the other BASELINE configs, the fused entry points, the
+reference's unmodified 6+6-layer BoxTransformer on the drop-in (configs[2]; baseline/ref_layers.py), module timings.
 
 --impl reference times that CPU formulation as the "reference arm": the reference has no CPU op
 (box_attn.h:53) and its CUDA extension cannot be installed offline against torch 2.11, so its own
