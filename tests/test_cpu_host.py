@@ -311,3 +311,17 @@ def test_torch_shim_loads_and_defers_to_python_for_unusual_inputs():
     import boxer_b200
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         boxer_b200.ops.box_attn_forward(v, sh, ls, loc, w, 64)
+
+
+def test_bench_compulsory_bytes_model():
+    """bench.py's `roofline_compulsory`: inputs read once, outputs written once."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = dict(B=1, S=22223, H=8, D=32, L=4, Nq=22223, P=16)
+    n = 22223 * 8 * 4 * 16
+    f = bench.compulsory(n, d, 0.176, 6555.5, False, 189_681_408)
+    b = bench.compulsory(n, d, 0.347, 6555.5, True, None)
+    assert f["bytes"] == 22223 * 256 * 4 * 2 + n * 12 == 182_050_816        # value + out + (loc, weight) per sample
+    assert b["bytes"] == 2 * f["bytes"] and "frac_measured_dram" not in b     # + grad_out, three gradients, the zero fill
+    assert f["frac"] == pytest.approx(182_050_816 / 0.176e-3 / 1e9 / 6555.5)
+    assert f["frac_measured_dram"] > f["frac"]
