@@ -158,11 +158,18 @@ def test_c5_bev_full_size(dtype):
     _box_case(W.bev_rotated(B=8, Nq=1000, K=3, size=468, device=DEV), dtype)
 
 
+@pytest.mark.parametrize("path", ["auto", "tile"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
-def test_c5_box3d_encoder_reference_exact(dtype):
+def test_c5_box3d_encoder_reference_exact(dtype, path):
     """The call BoxeR-3D's encoder layers actually make (box3d_transformer.py:233, base_boxer3d_detection.yaml:132-146):
-    234^2 + 117^2 BEV levels, D = 32, Nq = S = 68 445, 2x2 grid with the /2 divisor, per-head reference angles."""
+    234^2 + 117^2 BEV levels, D = 32, Nq = S = 68 445, 2x2 grid with the /2 divisor, per-head reference angles.
+    path "tile": the same through the query-tile x value-tile kernels (two levels, rotated 2 x 2 grids)."""
     from boxer_b200 import workloads as W
+    b = _ops()
     w = W.box3d_encoder(device=DEV)
     assert w.dims == dict(B=1, S=68445, H=8, D=32, L=2, Nq=68445, P=4)
-    _box_case(w, dtype)
+    b.ops.set_kernel_path(path)
+    try:
+        _box_case(w, dtype)
+    finally:
+        b.ops.set_kernel_path("auto")
