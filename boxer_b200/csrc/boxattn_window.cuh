@@ -64,10 +64,12 @@ constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 // (pixel offset, float weight) pairs, one lane per slot, and the walk reads two pairs per 16-byte shared load --
 // the per-slot index arithmetic (row wrap, int -> float, scaling: 9 of the 16 instructions a slot costs) is done
 // once per slot instead of once per slot and lane.  Measured (r02a, K=4 encoder forward): bf16 0.1988 -> 0.1858 ms,
-// fp32 at 28 warps / 72 registers 0.1786 -> 0.1865 ms (the table adds a shared-memory round trip to every pass and
-// the fp32 kernel waits on latency, not on issue slots).  BXR_FWD_TAB: 0 off, 1 all types, 2 all but fp32 (default).
+// fp32 at 28 warps / 72 registers 0.1786 -> 0.1865 ms at the time (20 bytes of spill).  Re-measured in round 2 (r02x), after
+// the corner table had put the table walk into the fp32 kernels anyway and the in-register walk's row-wrap arithmetic had
+// been identified as ~10 % of the forward by ablation: fp32 K=4 0.1728 -> 0.1548 ms, trained-like 0.303 -> 0.247, K=2
+// 0.088 -> 0.076 -- adopted.  BXR_FWD_TAB: 0 off, 1 all types (default), 2 all but fp32.
 #ifndef BXR_FWD_TAB
-#define BXR_FWD_TAB 2
+#define BXR_FWD_TAB 1
 #endif
 template <typename TV>
 struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD_TAB == 2 && !std::is_same<TV, float>::value); };
@@ -78,9 +80,9 @@ struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD
 #ifndef BXR_FWD_CTAB
 #define BXR_FWD_CTAB 1
 #endif
-// BXR_BWD_TAB: the backward walk from a slot table like the bf16 forward's.  0 off, 1 all types, 2 all but fp32 (default).
-// Measured r02l (K=4 encoder backward): bf16 0.4118 -> 0.3946 ms, fp32 0.3526 -> 0.3767 ms (as in the forward, the extra
-// shared-memory round trip per pass costs the fp32 kernel more than the saved instructions buy).  One lane per slot writes (offset relative to the
+// BXR_BWD_TAB: the backward walk from a slot table like the forward's.  0 off, 1 all types, 2 (default) see TABB below.
+// Measured r02l (K=4 encoder backward, before the corner table): bf16 0.4118 -> 0.3946 ms, fp32 0.3526 -> 0.3767 ms;
+// r02x (with it): fp32 0.3452 -> 0.3418 ms, trained-like 0.636 -> 0.557.  One lane per slot writes (offset relative to the
 // lane's base pointers, float weight) after the scatter.  The walk then
 // needs no row-wrap arithmetic, no flag read, no int -> float scaling per lane, and no group barrier before the
 // d totals overwrite the flag window (the flags are consumed when the table is built).  An untouched pixel is marked by
@@ -101,6 +103,9 @@ struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD
 // 0.1846 -> 0.1794 ms, uniform 0.382 -> 0.362 ms; backward 1 -> 4: 0.365 -> 0.350 ms, 8 is worse there)
 #ifndef BXR_BWD_CTAB
 #define BXR_BWD_CTAB 1
+#endif
+#ifndef BXR_DIAG
+#define BXR_DIAG 0
 #endif
 #ifndef BXR_FB_UNROLL
 #define BXR_FB_UNROLL 8
@@ -547,6 +552,9 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                     w.nx = __shfl_sync(kFullMask, me.nx, src, G); w.ny = __shfl_sync(kFullMask, me.ny, src, G);
                     w.ke = __shfl_sync(kFullMask, me.ke, src, G); w.mode = __shfl_sync(kFullMask, me.mode, src, G);
                 }
+#if BXR_DIAG == 7
+                if (w.mode >= 0) { acc[0] += (float)w.nx; continue; }      // DIAGNOSTIC: phases A + B only
+#endif
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
                 const int lh = lv.h[l], lw = lv.w[l];
@@ -571,7 +579,13 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                         float v[4][VEC];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
+#if BXR_DIAG == 11
+                            if (tw[j] != 0.f) V::load16(vlane, (unsigned)j, v[j]);      // DIAGNOSTIC (wrong results): gathers hit the same lines
+#elif BXR_DIAG == 13
+                            if (tw[j] != 0.f) { v[j][0] = v[j][1] = v[j][2] = v[j][3] = __uint_as_float(to[j]); }   // DIAGNOSTIC: no gather
+#else
                             if (tw[j] != 0.f) V::load16(vlane, to[j], v[j]);
+#endif
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (tw[j] != 0.f) {
@@ -596,18 +610,32 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                         unsigned offs[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+#if BXR_DIAG == 4
+                            offs[j] = off + (unsigned)(q + j) * HDV;      // DIAGNOSTIC (wrong pixels): no row wrap
+#else
                             offs[j] = off;
                             off += HDV;
                             if (++ix == w.nx) { ix = 0; off += row_skip; }
+#endif
                         }
                         float v[4][VEC];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
+#if BXR_DIAG == 1
+                            if (wi[j] != 0) V::load16(vbase, vlev + (unsigned)j, v[j]);   // DIAGNOSTIC (wrong results): every gather hits the same lines
+#elif BXR_DIAG == 3
+                            if (wi[j] != 0) { v[j][0] = v[j][1] = v[j][2] = v[j][3] = __uint_as_float(offs[j]); }   // DIAGNOSTIC: no gather at all
+#else
                             if (wi[j] != 0) V::load16(vbase, offs[j], v[j]);   // slots past nq were zeroed and never written
+#endif
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (wi[j] != 0) {
+#if BXR_DIAG == 5
+                                const float wv = __int_as_float(wi[j]) * inv_scale;      // DIAGNOSTIC (wrong values): no int -> float conversion
+#else
                                 const float wv = (float)wi[j] * inv_scale;
+#endif
 #pragma unroll
                                 for (int i = 0; i < VEC; ++i) acc[i] += wv * v[j][i];
                             }
@@ -705,7 +733,9 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     __shared__ LevelTable lv;
     __shared__ __align__(16) int s_win[GROUPS * kWinPitch];     // pixel weights W[pix], fixed point
     __shared__ __align__(16) float s_dot[GROUPS * kWinPitch];   // "touched" flag, then d[pix] = <grad_out, value[pix]>
-    constexpr bool TABB = (BXR_BWD_TAB == 1 || (BXR_BWD_TAB == 2 && !std::is_same<TV, float>::value)) && G >= 8;     // G = 4: 64 groups per CTA, the table would not fit 48 KB
+    // 2 (default): every type except the fp32 two-levels-per-pass kernels of 2 x 2 grids (r02x: fp32 K=4 0.3452 -> 0.3418 ms,
+    // trained-like 0.636 -> 0.557; K=2 0.1844 -> 0.1923 loses)
+    constexpr bool TABB = (BXR_BWD_TAB == 1 || (BXR_BWD_TAB == 2 && (!std::is_same<TV, float>::value || LPP == 1))) && G >= 8;     // G = 4: 64 groups per CTA, the table would not fit 48 KB
     // BXR_BWD_CTAB: wide footprints (the per-point mode) as a window whose slots are the 4 P corners: each lane writes its
     // points' corners as table entries, the group walks them like a window's slots (d per corner by transpose reduction,
     // one scatter per corner) and every lane finishes its own points from the d entries -- instead of 6 broadcast shuffles
@@ -868,6 +898,9 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
                     w.nx = __shfl_sync(kFullMask, me.nx, src, G); w.ny = __shfl_sync(kFullMask, me.ny, src, G);
                     w.ke = __shfl_sync(kFullMask, me.ke, src, G); w.mode = __shfl_sync(kFullMask, me.mode, src, G);
                 }
+#if BXR_DIAG == 23
+                if (w.mode >= 0) continue;      // DIAGNOSTIC: no walk (phases A, B, D only)
+#endif
                 if (w.mode == 0) continue;
                 const int l = l0 + sl;
                 const int lh = lv.h[l], lw = lv.w[l];
@@ -899,7 +932,11 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (to[j] != kAbsent) {      // a touched pixel / an existing corner
+#if BXR_DIAG == 22
+                                v[j][0] = v[j][1] = v[j][2] = v[j][3] = __uint_as_float(to[j]);      // DIAGNOSTIC: no gather
+#else
                                 V::load16(tvp, to[j], v[j]);
+#endif
                             } else {
 #pragma unroll
                                 for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
@@ -912,7 +949,9 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
                             dsum[j] = t;
+#if BXR_DIAG != 21
                             if (to[j] != kAbsent && tw[j] != 0.f) scatter_row<ACC, VEC>(tgp + (size_t)to[j] * VEC, go, tw[j], dscale);   // NaN weights propagate
+#endif
                         }
                         float total;
                         const int mine = reduce4<G>(dsum, total, lane, gm);
