@@ -72,6 +72,34 @@ def ncu_issue():
         return None, None
 
 
+def l2_reduction_peak():
+    """Payload rate (GB/s) of `red.global.add.v4.f32` at the backward scatter's access shape: measured live with the
+    microbenchmark binary when it is there (scripts/microbench/red_throughput, built by __graft_entry__.build()), else
+    the committed measurement in profiles/traffic.json."""
+    exe = os.path.join(ROOT, "scripts", "microbench", "red_throughput")
+    try:
+        if os.access(exe, os.X_OK):
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+            return float(json.loads(out)["red_v4_random_22.8MB"]), "measured live (scripts/microbench/red_throughput)"
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return float(t["l2_red_peak_gbs"]), t.get("l2_red_peak_source")
+    except Exception:
+        return None, None
+
+
+def ncu_red_bytes():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get("bwd_red_bytes"), t.get("bwd_red_bytes_source")
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -765,6 +793,18 @@ def main():
     win_frac = {"box": W.window_mode_fraction(sets[0][0]), "trained": W.window_mode_fraction(trn[0][0])}
     del trn
 
+    def l2_red(ms):
+        peak, src = l2_reduction_peak() if rank == 0 else (None, None)
+        nbytes, bsrc = ncu_red_bytes()
+        if not peak or not nbytes:
+            return None
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "l2_reduction", "kernel": "box_bwd_win_kernel<float,G=8,SUB=8,PPL=2,atomic>", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "red_bytes": nbytes, "red_bytes_source": bsrc, "peak_source": src,
+                "ms_per_launch": ms,
+                "note": "the scatter alone would take red_bytes / peak; an ablation build without it runs 0.239 ms "
+                        "(profiles/r02xy_ablation.json): the backward sits between its two bounds, reductions and issue slots"}
+
     def dram(tr, ms):      # measured DRAM bytes of the committed ncu capture over the live launch time
         return None if tr is None else {"GBs": tr / (ms * 1e-3) / 1e9, "frac_of_peak": tr / (ms * 1e-3) / 1e9 / bw_peak}
 
@@ -804,6 +844,10 @@ def main():
             "note": "frac = compulsory bytes / kernel time / peak; frac_measured_dram = ncu DRAM bytes of the committed capture / "
                     "live kernel time / peak.  These, not the no-reuse model above, say how far the kernels are from the HBM bound: "
                     "value (22.8 MB) is L2-resident, so the kernels are bound by instruction issue and gather latency"},
+        # the resource the backward's scatter is bound by: one red.v4 per lane per unique pixel goes to the L2's reduction
+        # units, whose payload rate is far below the L2's load bandwidth (microbenchmark: 6.4 TB/s against 17 TB/s of
+        # 128-byte line gathers).  bytes = RED instructions executed (ncu, committed capture) x 16 B, identical inputs.
+        "roofline_l2_reduction": l2_red(kb_ms),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                 "host_cpus": ("NUMA-local to the GPU: %d cpus" % len(local)) if local else "unpinned",

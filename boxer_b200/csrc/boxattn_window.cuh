@@ -120,6 +120,15 @@ struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD
 #ifndef BXR_UNIT_REVERSE
 #define BXR_UNIT_REVERSE 1
 #endif
+// Software-pipelined point loads in the fp32 one-level-per-pass forward: the next level's (at the last level: the next
+// work unit's) locations / weights are requested before the current level is walked.  The first use of a level's points
+// was the longest single stall of the kernel (ncu r02z: 12 % of the stall samples on 0.5 % of the instructions); r02pf:
+// K=4 forward 0.1558 -> 0.1508 ms, trained-like 0.248 -> 0.2375, uniform 0.301 -> 0.295.  The backward (+4 %: it is bound
+// by the L2 reduction rate, not by this latency), the two-levels-per-pass kernels (+4 %) and bf16 (+5 %) lose and keep the
+// plain loads; prefetch.global.L2 / .L1 of the next unit's rows instead: forward -1.6 %, backward +2.6 %, not adopted.
+#ifndef BXR_FWD_PIPE
+#define BXR_FWD_PIPE 1
+#endif
 constexpr int kFbUnroll = BXR_FB_UNROLL;
 constexpr int kFbUnrollBwd = BXR_FB_UNROLL_BWD;
 // table entry of a pixel nobody touched / a corner outside the level (valid offsets stay below it: use_window())
@@ -201,6 +210,20 @@ __device__ __forceinline__ LanePoint lane_point(const float* __restrict__ loc_l,
     const int pc = act ? pt : 0;
     const float2 xy = __ldg(reinterpret_cast<const float2*>(loc_l) + pc);
     return lane_point_xy(xy.x, xy.y, __ldg(w_l + pc), act, h, w);
+}
+
+// the loads of lane_point alone, for the software-pipelined forward (BXR_FWD_PIPE): the next level's (at the last
+// level: the next work unit's) points are requested before the current level is walked
+struct RawPoint {
+    float2 xy;
+    float aw;
+};
+__device__ __forceinline__ RawPoint raw_point(const float* __restrict__ loc_l, const float* __restrict__ w_l, int pt, int P) {
+    const int pc = pt < P ? pt : 0;
+    RawPoint r;
+    r.xy = __ldg(reinterpret_cast<const float2*>(loc_l) + pc);
+    r.aw = __ldg(w_l + pc);
+    return r;
 }
 
 // One (row, level) box of the fused entry points: the K x K grid of BoxAttention._where_to_attend
@@ -418,6 +441,15 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
     const float* __restrict__ loc = static_cast<const float*>(p.loc);
     const float* __restrict__ w0 = static_cast<const float*>(p.w0);
 
+    constexpr bool PIPE = BXR_FWD_PIPE != 0 && !FUSED && !TILED && LPP == 1 && std::is_same<TV, float>::value;
+    RawPoint nxt[PPL];
+    if constexpr (PIPE) {
+        const long long r0 = (long long)(BXR_UNIT_REVERSE ? n_units - 1 - (int)blockIdx.x : (int)blockIdx.x) * GROUPS + gid;
+        const long long r0c = (r0 >= 0 && r0 < p.rows) ? r0 : 0;
+        const int lc0 = sub < p.L ? sub : 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) nxt[k] = raw_point(loc + r0c * p.LP * 2 + lc0 * p.P * 2, w0 + r0c * p.LP + lc0 * p.P, slane + k * SUB, p.P);
+    }
     // units are dealt round-robin: rows of the coarse levels (wide windows -> per-point fallback) cost
     // several times more than level-0 rows, and a contiguous split leaves the CTAs that own them as a tail
 #if BXR_UNIT_REVERSE
@@ -458,6 +490,7 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
             for (int k = 0; k < PPL; ++k) {
                 const int ptn = lact ? slane + k * SUB : p.P;
                 if constexpr (FUSED) pt[k] = lane_point_box<SMAX>(lbx, static_cast<const float*>(p.kidx), w_row + lmc * p.P, ptn, p.P, mh, mw, rsm);
+                else if constexpr (PIPE) pt[k] = lane_point_xy(nxt[k].xy.x, nxt[k].xy.y, nxt[k].aw, ptn < p.P, mh, mw);
                 else pt[k] = lane_point(loc_row + lmc * p.P * 2, w_row + lmc * p.P, ptn, p.P, mh, mw);
                 if constexpr (SMAX) {
                     if (ptn < p.P) static_cast<float*>(p.attn_out)[row * p.LP + lmc * p.P + ptn] = pt[k].aw;
@@ -467,6 +500,16 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                     by0 = min(by0, pt[k].y0); by1 = max(by1, pt[k].y0 + 1);
                     S += fabsf(pt[k].aw);
                 }
+            }
+            if constexpr (PIPE) {
+                // request the next pass's points now: the next level of this row, or level 0 of the next unit's row
+                const bool last = l0 + LPP >= p.L;
+                const long long nrow = row_raw + (BXR_UNIT_REVERSE ? -1LL : 1LL) * (long long)gridDim.x * GROUPS;
+                const long long rn = last ? ((nrow >= 0 && nrow < p.rows) ? nrow : row) : row;
+                const int ln = (last ? 0 : l0 + LPP) + sub;
+                const int lnc = ln < p.L ? ln : 0;
+#pragma unroll
+                for (int k = 0; k < PPL; ++k) nxt[k] = raw_point(loc + rn * p.LP * 2 + lnc * p.P * 2, w0 + rn * p.LP + lnc * p.P, slane + k * SUB, p.P);
             }
             SubWin me;
             me.X0 = max(smin<SUB>(bx0, kFullMask), 0); me.Y0 = max(smin<SUB>(by0, kFullMask), 0);

@@ -8,11 +8,13 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv > $OUT/gpu.csv 2>&1
 nproc > $OUT/host.txt; grep -m1 "model name" /proc/cpuinfo >> $OUT/host.txt
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
-timeout 900 python -m pytest tests -m gpu -q --maxfail=12 --timeout 600 > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log
+timeout 1300 python -m pytest tests -m gpu -q --maxfail=12 --timeout 900 --durations=10 > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log
 tail -5 $OUT/pytest.log
 timeout 600 python bench.py --variants > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 cat $OUT/bench.json; tail -30 $OUT/bench.err
 cp gpurun_out/variants.json $OUT/variants.json 2>/dev/null
+[ -x scripts/microbench/red_throughput ] && scripts/microbench/red_throughput | tee $OUT/red_throughput.json
+python scripts/host_overhead.py $OUT/host_overhead.json 2>&1 | tail -6
 timeout 300 python scripts/compare_reference_cuda.py $OUT/vs_reference_cuda.json > $OUT/vs_reference_cuda.log 2>&1; tail -8 $OUT/vs_reference_cuda.log
 if [ "$MODE" != "quick" ]; then
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:attn_|box_|absmax|finalize|det_scale" -c 400 --csv --log-file $OUT/launches.csv \
