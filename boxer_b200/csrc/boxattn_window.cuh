@@ -120,6 +120,13 @@ struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD
 #ifndef BXR_UNIT_REVERSE
 #define BXR_UNIT_REVERSE 1
 #endif
+// 4-entry batches of the forward table walk in flight (r02un: fp32 K=4 box forward 0.1498 (2) -> 0.1469 (1) -> 0.158 (4) ms,
+// K=2 0.0750 -> 0.0739, bf16 0.1579 -> 0.1556; uniform points 0.2938 (2) -> 0.2977 (1) -> 0.2871 (4)).  One loop for both
+// table kinds: a separate loop per kind, each with its own unroll factor, cost 18 % (r02uw: 72 registers + spill).
+#ifndef BXR_FWD_TAB_UNROLL
+#define BXR_FWD_TAB_UNROLL 1
+#endif
+constexpr int kFwdTabUnroll = BXR_FWD_TAB_UNROLL;
 // Software-pipelined point loads in the fp32 one-level-per-pass forward: the next level's (at the last level: the next
 // work unit's) locations / weights are requested before the current level is walked.  The first use of a level's points
 // was the longest single stall of the kernel (ncu r02z: 12 % of the stall samples on 0.5 % of the instructions); r02pf:
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(kFwdThreads, fwd_min_blocks(Vec16<TV>::VEC, PP
                     // per-lane base pointer in registers: the table offsets are the same for all lanes of the group
                     const typename V::Raw* vlane = static_cast<const typename V::Raw*>(value16) + vrow;
                     asm volatile("" : "+l"(vlane));      // keep it a register pair: one IMAD.WIDE per load, no re-derivation
-#pragma unroll 2
+#pragma unroll kFwdTabUnroll
                     for (int q = 0; q < wq_n; q += 4) {
                         const uint4 t0 = *reinterpret_cast<const uint4*>(ct + q);
                         const uint4 t1 = *reinterpret_cast<const uint4*>(ct + q + 2);
