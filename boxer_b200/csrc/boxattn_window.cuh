@@ -123,6 +123,12 @@ struct FwdSlotTable { static constexpr bool value = BXR_FWD_TAB == 1 || (BXR_FWD
 // 4-entry batches of the forward table walk in flight (r02un: fp32 K=4 box forward 0.1498 (2) -> 0.1469 (1) -> 0.158 (4) ms,
 // K=2 0.0750 -> 0.0739, bf16 0.1579 -> 0.1556; uniform points 0.2938 (2) -> 0.2977 (1) -> 0.2871 (4)).  One loop for both
 // table kinds: a separate loop per kind, each with its own unroll factor, cost 18 % (r02uw: 72 registers + spill).
+// backward slot table in the deterministic kernels: 0 never (default), 1 like the atomic kernels, 2 bf16 only.  With the
+// table the 64-bit reductions of a 4-slot batch leave back to back and the LSU-bound kernel loses 25 % (r02dt: fp32 2.08 ->
+// 2.59 ms, bf16 2.12 -> 2.60, trained-like 3.5 -> 4.27)
+#ifndef BXR_BWD_TAB_DET
+#define BXR_BWD_TAB_DET 0
+#endif
 #ifndef BXR_FWD_TAB_UNROLL
 #define BXR_FWD_TAB_UNROLL 1
 #endif
@@ -785,7 +791,9 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
     __shared__ __align__(16) float s_dot[GROUPS * kWinPitch];   // "touched" flag, then d[pix] = <grad_out, value[pix]>
     // 2 (default): every type except the fp32 two-levels-per-pass kernels of 2 x 2 grids (r02x: fp32 K=4 0.3452 -> 0.3418 ms,
     // trained-like 0.636 -> 0.557; K=2 0.1844 -> 0.1923 loses)
-    constexpr bool TABB = (BXR_BWD_TAB == 1 || (BXR_BWD_TAB == 2 && (!std::is_same<TV, float>::value || LPP == 1))) && G >= 8;     // G = 4: 64 groups per CTA, the table would not fit 48 KB
+    // The deterministic scatter (64-bit integer reductions, LSU-bound) keeps the in-register walk (BXR_BWD_TAB_DET).
+    constexpr bool TABB = (BXR_BWD_TAB == 1 || (BXR_BWD_TAB == 2 && (!std::is_same<TV, float>::value || LPP == 1))) && G >= 8     // G = 4: 64 groups per CTA, the table would not fit 48 KB
+                          && (!DET || BXR_BWD_TAB_DET == 1 || (BXR_BWD_TAB_DET == 2 && !std::is_same<TV, float>::value));
     // BXR_BWD_CTAB: wide footprints (the per-point mode) as a window whose slots are the 4 P corners: each lane writes its
     // points' corners as table entries, the group walks them like a window's slots (d per corner by transpose reduction,
     // one scatter per corner) and every lane finishes its own points from the d entries -- instead of 6 broadcast shuffles
