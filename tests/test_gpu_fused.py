@@ -136,6 +136,37 @@ def test_fused_equals_unfused_on_the_same_device():
     assert helpers.rel_err(g_f[3], attn.grad) <= 2e-5
 
 
+def test_fused_accepts_odd_offset_views_of_the_small_operands():
+    """kernel_indices / valid_ratios / boxes that are contiguous views at an odd element offset (4-byte aligned only) used to
+    size the workspace for the fused kernels and then take the general path: BXR_ERR_WORKSPACE.  ops.py re-aligns them."""
+    import boxer_b200
+
+    def odd(t):         # same values, storage offset of one element
+        buf = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 8 != 0 and v.is_contiguous()
+        return v
+
+    for name in ("k2_ratios", "rot_k2_ratios_d64"):
+        c = _case(name)
+        out_ref, g_ref = _ours(c, torch.float32)
+        mv = lambda t: None if t is None else t.to(DEV, torch.float32).contiguous()
+        value = mv(c["value"]).requires_grad_(True)
+        boxes = odd(mv(c["boxes"])).requires_grad_(True)
+        angles = mv(c["angles"])
+        if angles is not None:
+            angles = odd(angles).requires_grad_(True)
+        attn = mv(c["attn"]).requires_grad_(True)
+        out = boxer_b200.BoxGridAttnFunction.apply(value, c["shapes"].to(DEV), c["start"].to(DEV), boxes, angles,
+                                                   odd(mv(c["vr"])), odd(mv(c["kidx"])), attn, 64)
+        out.backward(mv(c["go"]))
+        assert torch.equal(out.detach(), out_ref)
+        assert helpers.rel_err(boxes.grad, g_ref[1]) <= 1e-6
+        assert helpers.rel_err(attn.grad, g_ref[3]) <= 1e-6
+        assert helpers.rel_err(value.grad, g_ref[0]) <= 1e-5      # float atomics: order differs run to run
+
+
 def test_fused_deterministic_and_paths_agree():
     import boxer_b200
     c = _case("rot_k2_ratios_d64")
