@@ -719,6 +719,7 @@ def main():
     if dist_on:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line only (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
