@@ -47,10 +47,17 @@ __device__ __forceinline__ BTap bcast_tap(const LanePoint& t, float lw, int src,
 #ifndef BXR_INST_FWD_MINB_F32
 #define BXR_INST_FWD_MINB_F32 3
 #endif
+// resident CTAs asked of the bf16 (8 channels per lane) forward and of the backward kernels
+#ifndef BXR_INST_FWD_MINB_BF16
+#define BXR_INST_FWD_MINB_BF16 2
+#endif
+#ifndef BXR_INST_BWD_MINB
+#define BXR_INST_BWD_MINB 2
+#endif
 
 // LB: levels held in registers per lane (L <= LB); LG: levels whose corner rows are in flight together
 template <typename TV, int G, int LB>
-__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_INST_FWD_MINB_F32) inst_fwd_own_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? BXR_INST_FWD_MINB_BF16 : BXR_INST_FWD_MINB_F32) inst_fwd_own_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
     constexpr int LG = BXR_INST_LG;
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_INST_
 #endif
 
 template <typename TV, int G, int LB, typename ACC>
-__global__ void __launch_bounds__(kThreads, 2) inst_bwd_own_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, BXR_INST_BWD_MINB) inst_bwd_own_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
     constexpr int LG = (VEC > 4) ? 1 : BXR_INST_BWD_LG;     // 8 channels per lane: no registers left for a second level (A/B, r01q)
@@ -367,7 +374,7 @@ __device__ __forceinline__ void inst_write_tap(InstTap* dst, const LanePoint& t,
 }
 
 template <typename TV, int G, int LB>
-__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_INST_FWD_MINB_F32) inst_fwd_tab_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? BXR_INST_FWD_MINB_BF16 : BXR_INST_FWD_MINB_F32) inst_fwd_tab_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
     constexpr int LG = BXR_INST_LG;
@@ -492,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, (Vec16<TV>::VEC > 4) ? 2 : BXR_INST_
 }
 
 template <typename TV, int G, int LB, typename ACC>
-__global__ void __launch_bounds__(kThreads, 2) inst_bwd_tab_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, BXR_INST_BWD_MINB) inst_bwd_tab_kernel(const AttnParams p) {
     using V = Vec16<TV>;
     constexpr int VEC = V::VEC;
     constexpr int GROUPS = kThreads / G;
