@@ -16,3 +16,9 @@ timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --error-ex
 grep -E "RACECHECK SUMMARY|passed|failed" $OUT/racecheck_inst.log | sort | uniq -c | head
 grep -E "RACECHECK SUMMARY|passed|failed" $OUT/racecheck.log | sort | uniq -c | head -20
 grep -E "hazard" $OUT/racecheck.log | sed -E 's/0x[0-9a-f]+/X/g; s/[0-9]+ bytes/N bytes/' | sort | uniq -c | sort -rn | head -12
+# optional third pass: uninitialised global reads and barrier misuse on the window / tile kernels
+if [ "$2" == "more" ]; then
+  timeout 900 compute-sanitizer --tool initcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py -q -x -k "$SEL2" -p no:cacheprovider > $OUT/initcheck.log 2>&1; echo "initcheck rc=$?" | tee -a $OUT/initcheck.log
+  timeout 900 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py -q -x -k "$SEL2" -p no:cacheprovider > $OUT/synccheck.log 2>&1; echo "synccheck rc=$?" | tee -a $OUT/synccheck.log
+  grep -E "ERROR SUMMARY|passed|failed" $OUT/initcheck.log $OUT/synccheck.log
+fi
