@@ -785,6 +785,7 @@ def main():
     uni = make_sets(dev, 1, seed0=rank_seed(rank) + 100, K=CFG["K"], dist="uniform", B=CFG["B_per_gpu"])
     uf_ms, ub_ms = kernel_times(ops, uni, 10)
     uf_ms, ub_ms = kernel_times(ops, uni, 20)
+    red_uni = W.backward_reduction_bytes(uni[0][0])
     del uni
     # third distribution: trained-like encoder boxes (per-query offsets, sizes log-uniform in 2..64 px) -- between the
     # init-state headline (every window fits the 64-pixel footprint) and uniform points (none does)
@@ -792,19 +793,27 @@ def main():
     tf_ms, tb_ms = kernel_times(ops, trn, 10)
     tf_ms, tb_ms = kernel_times(ops, trn, 20)
     win_frac = {"box": W.window_mode_fraction(sets[0][0]), "trained": W.window_mode_fraction(trn[0][0])}
+    red_trn = W.backward_reduction_bytes(trn[0][0])
+    red_box = W.backward_reduction_bytes(sets[0][0])
     del trn
 
-    def l2_red(ms):
-        peak, src = l2_reduction_peak() if rank == 0 else (None, None)
-        nbytes, bsrc = ncu_red_bytes()
-        if not peak or not nbytes:
+    red_peak, red_peak_src = l2_reduction_peak() if rank == 0 else (None, None)
+
+    def l2_red(ms, nbytes, full=False):
+        """The backward against the L2 reduction rate: payload bytes of the `red.v4`s it issues (counted on the host from
+        the workload, boxer_b200.workloads.backward_reduction_bytes) over the live launch time, against the microbenchmark."""
+        if not red_peak:
             return None
         ach = nbytes / (ms * 1e-3) / 1e9
-        return {"bound": "l2_reduction", "kernel": "box_bwd_win_kernel<float,G=8,SUB=8,PPL=2,atomic>", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "red_bytes": nbytes, "red_bytes_source": bsrc, "peak_source": src,
-                "ms_per_launch": ms,
-                "note": "the scatter alone would take red_bytes / peak; an ablation build without it runs 0.239 ms "
-                        "(profiles/r02xy_ablation.json): the backward sits between its two bounds, reductions and issue slots"}
+        r = {"achieved": ach, "frac": ach / red_peak, "red_bytes": nbytes, "ms_per_launch": ms}
+        if full:
+            ncu_bytes, bsrc = ncu_red_bytes()
+            r = dict({"bound": "l2_reduction", "kernel": "box_bwd_win_kernel<float,G=8,SUB=8,PPL=2,atomic>", "peak": red_peak,
+                      "unit": "GB/s", "peak_source": red_peak_src}, **r,
+                     red_bytes_ncu=ncu_bytes, red_bytes_ncu_source=bsrc,
+                     note="the scatter alone would take red_bytes / peak; an ablation build without it runs 0.239 ms "
+                          "(profiles/r02xy_ablation.json): the backward sits between its two bounds, reductions and issue slots")
+        return r
 
     def dram(tr, ms):      # measured DRAM bytes of the committed ncu capture over the live launch time
         return None if tr is None else {"GBs": tr / (ms * 1e-3) / 1e9, "frac_of_peak": tr / (ms * 1e-3) / 1e9 / bw_peak}
@@ -828,8 +837,10 @@ def main():
                          "unit": "GB/s", "frac": ach_f / bw_peak, "traffic": tr_f, "algorithmic_bytes": n_samples * bf, "bytes_per_sample": bf,
                          "ms_per_launch": kf_ms, "Gsamples_per_s": n_samples / kf_ms / 1e6, "dram": dram(tr_f, kf_ms), "issue_active_pct_ncu": is_f},
         "uniform_locations": {"fwd_ms": uf_ms, "bwd_ms": ub_ms, "fwdbwd_Gsamples_per_s": n_samples / (uf_ms + ub_ms) / 1e6,
+                              "bwd_l2_reduction": l2_red(ub_ms, red_uni),
                               "note": "same sizes, sampling points drawn uniformly in [0,1)^2 (no spatial structure)"},
         "trained_like_locations": {"fwd_ms": tf_ms, "bwd_ms": tb_ms, "fwdbwd_Gsamples_per_s": n_samples / (tf_ms + tb_ms) / 1e6,
+                                   "bwd_l2_reduction": l2_red(tb_ms, red_trn),
                                    "window_mode_fraction": win_frac["trained"], "window_mode_fraction_headline": win_frac["box"],
                                    "note": "same sizes; every (query, head, level) has its own box: centre = pixel centre +- U(1/2) box, "
                                            "width / height log-uniform in 2..64 px of level 0; window_mode_fraction = share of (row, level) "
@@ -848,7 +859,7 @@ def main():
         # the resource the backward's scatter is bound by: one red.v4 per lane per unique pixel goes to the L2's reduction
         # units, whose payload rate is far below the L2's load bandwidth (microbenchmark: 6.4 TB/s against 17 TB/s of
         # 128-byte line gathers).  bytes = RED instructions executed (ncu, committed capture) x 16 B, identical inputs.
-        "roofline_l2_reduction": l2_red(kb_ms),
+        "roofline_l2_reduction": l2_red(kb_ms, red_box, full=True),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                 "host_cpus": ("NUMA-local to the GPU: %d cpus" % len(local)) if local else "unpinned",

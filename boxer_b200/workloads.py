@@ -183,6 +183,44 @@ def window_mode_fraction(w: Workload, cap: int = 64):
     return float(torch.stack(fits).mean())
 
 
+def backward_reduction_bytes(w: Workload, cap: int = 64, line_bytes: int = None):
+    """Bytes of `red.global.add` payload the window backward issues into `grad_value` for this workload: per
+    (row, level) one reduction of a head's channel slice (D accumulators) per *unique* touched pixel with a non-zero
+    weight when the touched range fits the `cap`-slot window, one per in-range corner otherwise (boxattn_window.cuh,
+    phases B / C).  The L2 performs reductions at a fixed payload rate (scripts/microbench/red_throughput.cu) far below
+    its load bandwidth, which makes this the backward's roofline numerator.  Checked against ncu's count of executed
+    `RED.128`s on the headline workload (profiles/README.md r02zz: 1.552 GB measured, 1.58 GB here)."""
+    loc = w.loc.float()
+    attn = w.weights[0].reshape(loc.shape[:-1])
+    D = w.value.shape[-1]
+    line = line_bytes if line_bytes is not None else 4 * D          # fp32 accumulators (bf16 values accumulate in fp32 too)
+    total = 0
+    for l, (h, wd) in enumerate(w.shapes.tolist()):
+        x = loc[:, :, :, l, :, 0] * wd - 0.5
+        y = loc[:, :, :, l, :, 1] * h - 0.5
+        inside = (x > -1) & (y > -1) & (x < wd) & (y < h)
+        x0, y0 = torch.floor(x).long(), torch.floor(y).long()
+        big = 1 << 30
+        bx0 = torch.where(inside, x0, torch.full_like(x0, big)).amin(-1).clamp_min(0)
+        bx1 = torch.where(inside, x0 + 1, torch.full_like(x0, -big)).amax(-1).clamp_max(wd - 1)
+        by0 = torch.where(inside, y0, torch.full_like(y0, big)).amin(-1).clamp_min(0)
+        by1 = torch.where(inside, y0 + 1, torch.full_like(y0, -big)).amax(-1).clamp_max(h - 1)
+        area = (bx1 - bx0 + 1).clamp_min(0) * (by1 - by0 + 1).clamp_min(0)
+        lx, ly = x - x0, y - y0
+        pix, corners = [], 0
+        for dy in (0, 1):
+            for dx in (0, 1):
+                a, b = x0 + dx, y0 + dy
+                ok = inside & (a >= 0) & (a < wd) & (b >= 0) & (b < h)
+                wgt = attn[:, :, :, l] * (lx if dx else 1 - lx) * (ly if dy else 1 - ly)
+                pix.append(torch.where(ok & (wgt != 0), b * wd + a, torch.full_like(a, -1)))
+                corners = corners + ok.long().sum(-1)
+        srt = torch.cat(pix, -1).sort(-1).values
+        uniq = (srt[..., 1:] != srt[..., :-1]).sum(-1) + 1 - (srt[..., 0] == -1).long()
+        total += int(torch.where(area <= cap, uniq, corners).sum())
+    return total * line
+
+
 def box3d_encoder(B=1, K=2, heads=8, head_dim=32, levels=((234, 234), (117, 117)), seed=7, device="cuda", ref_size=4.0) -> Workload:
     """The reference-exact BoxeR-3D encoder call (note N1 / config c5): two BEV levels 234x234 + 117x117
     (base_boxer3d_detection.yaml:132-146), C=256 (D=32), Nq = S = 68 445, 2x2 grid with the /2 index divisor

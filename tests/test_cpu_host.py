@@ -325,3 +325,43 @@ def test_bench_compulsory_bytes_model():
     assert b["bytes"] == 2 * f["bytes"] and "frac_measured_dram" not in b     # + grad_out, three gradients, the zero fill
     assert f["frac"] == pytest.approx(182_050_816 / 0.176e-3 / 1e9 / 6555.5)
     assert f["frac_measured_dram"] > f["frac"]
+
+
+def test_backward_reduction_bytes_matches_a_brute_force_count():
+    """bench.py's roofline_l2_reduction numerator: one reduction per unique touched pixel where the touched range fits the
+    64-slot window, one per in-range corner where it does not (boxattn_window.cuh phases B / C), restated with loops."""
+    import math
+    import torch
+    from boxer_b200 import workloads as W
+    for dist in ("box", "uniform"):
+        w = W.coco_encoder(K=4, image=(64, 96), device="cpu", dist=dist, oob=0.1)
+        loc = w.loc[0, ::23]                   # a few queries are enough for the loops
+        sub = W.Workload(**{**w.__dict__, "loc": w.loc[:, ::23], "weights": tuple(t[:, ::23] for t in w.weights)})
+        D = w.value.shape[-1]
+        want = 0
+        for q in range(loc.shape[0]):
+            for h in range(loc.shape[1]):
+                for l, (hh, ww) in enumerate(w.shapes.tolist()):
+                    pix, corners, xs, ys = set(), 0, [], []
+                    for p in range(loc.shape[3]):
+                        x = float(loc[q, h, l, p, 0]) * ww - 0.5
+                        y = float(loc[q, h, l, p, 1]) * hh - 0.5
+                        x, y = float(torch.tensor(x, dtype=torch.float32)), float(torch.tensor(y, dtype=torch.float32))
+                        if not (x > -1 and y > -1 and x < ww and y < hh):
+                            continue
+                        x0, y0 = math.floor(x), math.floor(y)
+                        xs += [x0, x0 + 1]
+                        ys += [y0, y0 + 1]
+                        for dy in (0, 1):
+                            for dx in (0, 1):
+                                if 0 <= x0 + dx < ww and 0 <= y0 + dy < hh:
+                                    corners += 1
+                                    pix.add((y0 + dy, x0 + dx))
+                    if not xs:
+                        continue
+                    nx = min(max(xs), ww - 1) - max(min(xs), 0) + 1
+                    ny = min(max(ys), hh - 1) - max(min(ys), 0) + 1
+                    want += len(pix) if nx * ny <= 64 else corners
+        got = W.backward_reduction_bytes(sub)
+        # (a corner whose bilinear weight is exactly zero is skipped by the kernel and by the function, not by the loops)
+        assert abs(got - want * 4 * D) <= 0.01 * want * 4 * D, (dist, got, want * 4 * D)
