@@ -1007,7 +1007,11 @@ __global__ void __launch_bounds__(kBwdThreads, (Vec16<TV>::VEC > 4) ? 2 * (kThre
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) t += go[i] * v[j][i];
                             dsum[j] = t;
-#if BXR_DIAG != 21
+#if BXR_DIAG == 24
+                            if (to[j] != kAbsent && tw[j] != 0.f && ((q + j) % 5) >= 2) scatter_row<ACC, VEC>(tgp + (size_t)to[j] * VEC, go, tw[j], dscale);   // DIAGNOSTIC: 60 % of the reductions
+#elif BXR_DIAG == 25
+                            if (to[j] != kAbsent && tw[j] != 0.f && ((q + j) & 1)) scatter_row<ACC, VEC>(tgp + (size_t)to[j] * VEC, go, tw[j], dscale);   // DIAGNOSTIC: 50 % of the reductions
+#elif BXR_DIAG != 21
                             if (to[j] != kAbsent && tw[j] != 0.f) scatter_row<ACC, VEC>(tgp + (size_t)to[j] * VEC, go, tw[j], dscale);   // NaN weights propagate
 #endif
                         }
