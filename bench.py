@@ -535,6 +535,16 @@ def variants(ops, dev, bw_peak):
     """Extra measurements (stderr + gpurun_out/variants.json); not part of the contract line."""
     from boxer_b200 import workloads as W
     res = {}
+    red_peak, _ = l2_reduction_peak()
+
+    def red_frac(w, P, ms, instance=False):
+        """backward against the L2 reduction rate (see roofline_l2_reduction): window kernels merge a (row, level)'s corners per
+        unique pixel where the range fits the window (64 slots, 32 when two levels share a pass: P <= 4); the instance
+        kernels issue one reduction per in-range corner (cap=0)."""
+        if not red_peak:
+            return None
+        nbytes = W.backward_reduction_bytes(w, cap=0 if instance else (32 if P <= 4 else 64))
+        return nbytes / (ms * 1e-3) / 1e9 / red_peak
 
     def time_call(fn, reps=20):
         for _ in range(3):
@@ -563,7 +573,8 @@ def variants(ops, dev, bw_peak):
                 bb = W.bytes_per_sample(False, True, 32, 4, K * K, sz)
                 res[f"enc_K{K}_{dist}_{'f32' if dt == torch.float32 else 'bf16'}"] = {
                     "fwd_ms": tf, "bwd_ms": tb, "fwd_Gs": n / tf / 1e6, "fwdbwd_Gs": n / (tf + tb) / 1e6,
-                    "fwd_frac": n * bf / (tf * 1e-3) / 1e9 / bw_peak, "bwd_frac": n * bb / (tb * 1e-3) / 1e9 / bw_peak}
+                    "fwd_frac": n * bf / (tf * 1e-3) / 1e9 / bw_peak, "bwd_frac": n * bb / (tb * 1e-3) / 1e9 / bw_peak,
+                    "bwd_l2_reduction_frac": red_frac(w, K * K, tb)}
     for K in (14, 28):
         for dt in (torch.float32, torch.bfloat16):
             m = W.coco_mask_head(K=K, device=dev)
@@ -579,7 +590,8 @@ def variants(ops, dev, bw_peak):
             bb = W.bytes_per_sample(True, True, 32, 4, K * K, sz)
             res[f"mask_K{K}_{'f32' if dt == torch.float32 else 'bf16'}"] = {
                 "fwd_ms": tf, "bwd_ms": tb, "fwd_Gs": n / tf / 1e6, "fwdbwd_Gs": n / (tf + tb) / 1e6,
-                "fwd_frac": n * bf / (tf * 1e-3) / 1e9 / bw_peak, "bwd_frac": n * bb / (tb * 1e-3) / 1e9 / bw_peak}
+                "fwd_frac": n * bf / (tf * 1e-3) / 1e9 / bw_peak, "bwd_frac": n * bb / (tb * 1e-3) / 1e9 / bw_peak,
+                "bwd_l2_reduction_frac": red_frac(m, K * K, tb, instance=True)}
     r = W.bev_rotated(B=8, device=dev)
     go = torch.randn(8, 1000, 128, device=dev)
     tf = time_call(lambda: ops.box_attn_forward(r.value, r.shapes, r.level_start, r.loc, r.weights[0], 64))
