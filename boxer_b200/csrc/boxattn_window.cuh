@@ -62,14 +62,15 @@ constexpr int fwd_min_blocks(int vec, int ppl, bool fused, bool fp32, bool /*two
 constexpr int kBwdThreads = BXR_BWD_THREADS, kBwdMinB = BXR_BWD_MINB;
 // The fp32 one-level-per-pass backward of head_dim 32 with the atomic scatter runs 3 CTAs per SM (24 warps, 78 registers, no spill) since
 // the table walk: r02bw, 4 -> 3 CTAs: box 0.3395 -> 0.3301 ms, trained-like 0.558 -> 0.531, uniform 1.108 -> 1.047.  The
-// two-levels-per-pass kernels of 2 x 2 grids (uniform +9 %) and bf16 (+2 %) lose with it; the deterministic and the fused
-// variants and other head dims were not measured and keep 4.
+// two-levels-per-pass kernels of 2 x 2 grids (uniform +9 %) and bf16 (+2 %) lose with it; the fused-grid variants gain the
+// same (r02bf: 0.378 -> 0.356 ms, with the softmax 0.401 -> 0.378); the deterministic ones do not care (2.06 -> 2.05) and
+// other head dims were not measured: both keep 4.
 #ifndef BXR_BWD_MINB_F32_LPP1
 #define BXR_BWD_MINB_F32_LPP1 3
 #endif
-constexpr int bwd_min_blocks(int vec, bool fp32, bool one_level, bool det, bool fused) {
+constexpr int bwd_min_blocks(int vec, bool fp32, bool one_level, bool det) {
     return vec > 4 ? 2 * (kThreads / kBwdThreads)
-                   : ((fp32 && one_level && !det && !fused) ? BXR_BWD_MINB_F32_LPP1 : kBwdMinB);
+                   : ((fp32 && one_level && !det) ? BXR_BWD_MINB_F32_LPP1 : kBwdMinB);
 }
 // Forward window walk from a slot table: after the scatter, the lanes of the level turn the dense window into
 // (pixel offset, float weight) pairs, one lane per slot, and the walk reads two pairs per 16-byte shared load --
@@ -789,7 +790,7 @@ __device__ __forceinline__ int reduce4(float (&d)[4], float& total, int lane, un
 // SMAX (with FUSED): `w0` holds the softmax weights the forward wrote; the weight gradients are chained through
 // the softmax before they leave the kernel:  grad_logit = w * (grad_w - sum_row(w * grad_w)).
 template <typename TV, int G, int SUB, int PPL, typename ACC, bool FUSED, bool SMAX = false, bool TILED = false>
-__global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(Vec16<TV>::VEC, std::is_same<TV, float>::value, G == 8 && SUB == G, sizeof(ACC) == 8, FUSED)) box_bwd_win_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(Vec16<TV>::VEC, std::is_same<TV, float>::value, G == 8 && SUB == G, sizeof(ACC) == 8)) box_bwd_win_kernel(const AttnParams p) {
     static_assert(FUSED || !SMAX, "the softmax epilogue is built for the fused entry points only");
     using V = Vec16<TV>;
     using GEO = WinGeom<G, SUB>;
