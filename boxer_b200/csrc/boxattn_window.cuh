@@ -150,7 +150,8 @@ constexpr int kFwdTabUnroll = BXR_FWD_TAB_UNROLL;
 // was the longest single stall of the kernel (ncu r02z: 12 % of the stall samples on 0.5 % of the instructions); r02pf:
 // K=4 forward 0.1558 -> 0.1508 ms, trained-like 0.248 -> 0.2375, uniform 0.301 -> 0.295.  The backward (+4 %: it is bound
 // by the L2 reduction rate, not by this latency), the two-levels-per-pass kernels (+4 %) and bf16 (+5 %) lose and keep the
-// plain loads; prefetch.global.L2 / .L1 of the next unit's rows instead: forward -1.6 %, backward +2.6 %, not adopted.
+// plain loads (the backward again at its final 3 CTAs per SM / 78 registers: 0.3301 -> 0.3375 ms); prefetch.global.L2 / .L1 of the
+// next unit's rows instead: forward -1.6 %, backward +2.6 %, not adopted.
 #ifndef BXR_FWD_PIPE
 #define BXR_FWD_PIPE 1
 #endif
