@@ -34,7 +34,8 @@ namespace bxr {
 //             uniform locations 0.3627 -> 0.3465 ms against 256 x 3 = 24 warps at 80 registers; 32 warps (64
 //             registers) spill and lose (0.198 ms).
 //   backward: 256-thread CTAs, 4 per SM = 32 warps at 64 registers; 128-thread CTAs cost 3 % there (0.346 -> 0.356 ms),
-//             36 warps (56 registers) spill.
+//             36 warps (56 registers) spill.  Since the table walk the fp32 head_dim-32 one-level-per-pass kernels run 3 per
+//             SM instead (bwd_min_blocks below).
 // The 16-byte-lane bf16 instantiations (8 channels per lane) keep the equivalent of two 256-thread CTAs.
 #ifndef BXR_FWD_THREADS
 #define BXR_FWD_THREADS 128
