@@ -731,8 +731,18 @@ def main():
     if dist_on:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line only (NCCL prints its version banner there)
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the JSON line only: NCCL prints its version banner on fd 1 while the communicator comes up
+        # (init is eager with device_id; the barrier covers a lazy one), so fd 1 points at stderr for that long
+        sys.stdout.flush()
+        saved = os.dup(1)
+        try:
+            os.dup2(2, 1)
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     n_gpus = world
 
     from boxer_b200 import _native
